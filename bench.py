@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py -- AlexNet product-quantized forward throughput (images/s) on N B200s, the metric of BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one PQ forward pass (23 layers: 8 PQ layers + ReLU/LRN/pool/softmax) over B synthetic 227x227x3 images
+per GPU (default B = 256, BASELINE.json configs[2]; `--batch 1024` with --gpus 8 is configs[3]).  Images are
+batch-sharded, weights replicated, and for N > 1 the only exchange is one all-gather of the [B,1000] logits
+(NCCL over NVLink) inside the step.  One JSON line is printed by rank 0 (see the task contract):
+  value     device-resident images/s, whole job (inputs already in HBM), CUDA events, max over ranks
+  e2e       the same metric through the host-buffer C-ABI call qcnn_net_forward_h (pinned host in -> host out)
+  roofline  dominant kernel: algorithmic bytes / CUDA-event time vs the measured HBM peak (+ the smem-gather bound)
+  cpu_baseline  the reference's own CPU path timed on this box (rank 0, N = 1 only, bounded sample)
+`--impl reference` times the reference CPU implementation with all host cores instead (no GPU work at all).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+IMG_CHW = (3, 227, 227)
+IMG_LEN = 3 * 227 * 227
+# ENUM_LyrType order (reference include/CaffePara.h:26)
+CONV, POOL, FCNT, RELU, LORN, DRPT, SMAX = range(7)
+# (layerInd: (kind, S, K, d, dims...)) of the shipped quantized AlexNet
+ALEXNET_PQ = {0: ("conv", 1, 128, 8, (96, 11, 11), 3 * 121), 4: ("conv", 6, 128, 8, (256, 5, 5), 48 * 25),
+              8: ("conv", 32, 128, 8, (384, 3, 3), 256 * 9), 10: ("conv", 24, 128, 8, (384, 3, 3), 192 * 9),
+              12: ("conv", 24, 128, 8, (256, 3, 3), 192 * 9), 15: ("fc", 2304, 32, 4, (4096,), 9216),
+              18: ("fc", 1024, 32, 4, (4096,), 4096), 21: ("fc", 4096, 16, 1, (1000,), 4096)}
+REAL_DIR = os.path.join(ROOT, "oracle", "_ref", "data", "AlexNet", "Bin.Files")
+REAL_PFX = "bvlc_alexnet_aCaF"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic data
+# ---------------------------------------------------------------------------------------------------------------
+def lcg_tables(n):
+    """A[i], C[i] with s_{i+1..} : s_i = A[i]*s_0 + C[i] (mod 2^32) for the LCG s <- 1664525 s + 1013904223."""
+    a, c = np.uint64(1664525), np.uint64(1013904223)
+    mask = np.uint64(0xFFFFFFFF)
+    A = np.empty(n, np.uint64)
+    Cc = np.empty(n, np.uint64)
+    A[0], Cc[0] = a, c
+    m = 1
+    while m < n:
+        k = min(m, n - m)
+        # step m+i = (step m) after (step i):  A = A[i]*A[m-1]..., composed as affine maps
+        A[m:m + k] = (A[:k] * A[m - 1]) & mask
+        Cc[m:m + k] = (A[:k] * Cc[m - 1] + Cc[:k]) & mask
+        m += k
+    return A, Cc
+
+
+def lcg_images(n, seed0, tables=None):
+    """image i has seed seed0+i; x = ((s>>8)&0xFFFF)/65536*256 - 128 after every update."""
+    A, Cc = tables if tables is not None else lcg_tables(IMG_LEN)
+    out = np.empty((n, IMG_LEN), np.float32)
+    mask = np.uint64(0xFFFFFFFF)
+    for i in range(n):
+        s = (A * np.uint64((seed0 + i) & 0xFFFFFFFF) + Cc) & mask
+        out[i] = ((s >> np.uint64(8)) & np.uint64(0xFFFF)).astype(np.float32) / np.float32(65536.0) * np.float32(256.0) \
+            - np.float32(128.0)
+    return out.reshape((n,) + IMG_CHW)
+
+
+def write_synthetic_alexnet(q, dirpath, pfx, seed=1):
+    """Random-init parameters of the AlexNet PQ architecture in the reference's .bin/.cbn formats, written with the
+    product's own writers (qcnn_write_bin_f32 / qcnn_write_cbn_u8).  Codebooks ~ N(0, 1/fan_in), assignments uniform."""
+    rng = np.random.RandomState(seed)
+    os.makedirs(dirpath, exist_ok=True)
+    for l, (kind, S, K, d, odims, fan) in sorted(ALEXNET_PQ.items()):
+        nout = odims[0]
+        asmt = rng.randint(0, K, size=tuple(odims) + (S,)).astype(np.uint8)
+        bias = (rng.randn(nout) * 0.05).astype(np.float32)
+        ctrd = (rng.randn(S, K, d) * (1.0 / np.sqrt(fan))).astype(np.float32)
+        if l == 21:
+            ctrd *= np.float32(0.25)  # keep logits inside expf range: the reference softmax has no max subtraction
+        bits = int(np.ceil(np.log2(K)))
+        base = os.path.join(dirpath, pfx)
+        q.write_bin_f32("%s.biasVec.%02d.bin" % (base, l + 1), bias)
+        q.write_bin_f32("%s.ctrdLst.%02d.bin" % (base, l + 1), ctrd)
+        q.write_cbn_u8("%s.asmtLst.%02d.cbn" % (base, l + 1), asmt, bits)
+
+
+def model_files(q, tmpdir):
+    """The reference's shipped AlexNet files when they were staged next to the compiled reference, else synthetic."""
+    if os.path.exists(os.path.join(REAL_DIR, REAL_PFX + ".asmtLst.22.cbn")):
+        return REAL_DIR, REAL_PFX, "shipped quantized AlexNet (bvlc_alexnet_aCaF)"
+    write_synthetic_alexnet(q, tmpdir, "synth")
+    return tmpdir, "synth", "random-init AlexNet PQ architecture"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU reference legs (the only place bench.py touches oracle/)
+# ---------------------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    dirpath, pfx, seed0, count = args
+    from oracle import pyoracle as po
+    net = _ref_worker.net if getattr(_ref_worker, "key", None) == (dirpath, pfx) else None
+    if net is None:
+        if po.have_ref():
+            net = po.RefNet(dirpath, pfx)
+        else:
+            net = ("port", po.alexnet_layers(), po.load_model(dirpath, pfx, po.alexnet_layers()))
+        _ref_worker.net, _ref_worker.key = net, (dirpath, pfx)
+    imgs = po.lcg_images(count, seed0)
+    t0 = time.perf_counter()
+    acc = 0.0
+    for i in range(count):
+        if isinstance(net, tuple):
+            p = po.net_forward(net[1], net[2], imgs[i:i + 1])[0]
+        else:
+            p = net.forward(imgs[i])
+        acc += float(p[0])
+    return time.perf_counter() - t0, acc
+
+
+def cpu_reference_single_thread(dirpath, pfx, images, warmup=2):
+    """The reference's CalcFeatMap path, ONE pinned thread, batch 1 (it has no batching: kDataCntInBatch = 1)."""
+    from oracle import pyoracle as po
+    try:
+        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[-1]})
+    except (AttributeError, OSError):
+        pass
+    kind = "reference" if po.have_ref() else "port"
+    imgs = po.lcg_images(min(images, 8), 12345)
+    if kind == "reference":
+        net = po.RefNet(dirpath, pfx)
+        tot, each = net.time_forward(imgs, warmup, images)
+        net.close()
+        ms = np.asarray(each)
+    else:
+        layers = po.alexnet_layers()
+        params = po.load_model(dirpath, pfx, layers)
+        ms = []
+        for i in range(warmup + images):
+            t0 = time.perf_counter()
+            po.net_forward(layers, params, imgs[i % len(imgs):i % len(imgs) + 1])
+            if i >= warmup:
+                ms.append((time.perf_counter() - t0) * 1e3)
+        ms = np.asarray(ms)
+    try:
+        os.sched_setaffinity(0, set(range(os.cpu_count())))
+    except (AttributeError, OSError):
+        pass
+    return kind, float(np.median(ms)), float(ms.min())
+
+
+def run_reference_arm(args, q):
+    """--impl reference: the reference CPU implementation on all host cores (one process per core, batch 1 each)."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import pyoracle as po
+    tmp = tempfile.mkdtemp(prefix="qcnn_ref_")
+    dirpath, pfx, what = model_files(q, tmp)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_core = 2
+    sample = cores * per_core          # images per step
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        def step(seed):
+            jobs = [(dirpath, pfx, seed + c * per_core, per_core) for c in range(cores)]
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, jobs, chunksize=1)
+            return time.perf_counter() - t0
+        for w in range(args.warmup):
+            step(1000 + w * sample)
+        times = [step(5000 + k * sample) for k in range(args.steps)]
+    total = float(np.sum(times))
+    value = sample * args.steps / total
+    kind = "reference" if po.have_ref() else "port"
+    line = {
+        "impl": "reference", "metric": "alexnet_pq_forward_images_per_s", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, what, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": "%d images per step (%d per core, batch 1 each, one process per core), %d steps"
+                                   % (sample, per_core, args.steps)},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, what, world):
+    return {"workload": "AlexNet PQ forward (CalcFeatMap_ConvAprx/_FCntAprx path), batch %d per GPU, synthetic "
+                        "227x227x3 LCG images" % args.batch,
+            "global_batch": args.batch * world, "per_gpu_batch": args.batch, "parallelism": "dp%d" % world,
+            "weights": what, "collective": "all_gather(logits [B,1000])" if world > 1 else "none",
+            "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; two input sets alternate" % (args.batch * IMG_LEN * 4 / 1e6)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200_arm(args, q):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B = args.batch
+
+    tmp = tempfile.mkdtemp(prefix="qcnn_bench_r%d_" % rank)
+    dirpath, pfx, what = model_files(q, tmp)
+    ctx = q.Context(local)
+    net = q.Net(ctx, dirpath, pfx, "AlexNet")
+
+    # two alternating input sets per rank (distinct images per rank), generated on the host, pinned
+    tables = lcg_tables(IMG_LEN)
+    host_in = [torch.from_numpy(lcg_images(B, 12345 + (rank * 2 + s) * B, tables)).pin_memory() for s in range(2)]
+    dev_in = [h.to(dev, non_blocking=False) for h in host_in]
+    host_out = torch.empty((B, 1000), dtype=torch.float32).pin_memory()
+    prob = torch.empty((B, 1000), dtype=torch.float32, device=dev)
+    logits = torch.empty((B, 1000), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * B, 1000), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(i):
+        net.forward(dev_in[i & 1], prob=prob, logits=logits)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logits)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(max(args.warmup, 3)):
+        step(w)
+    barrier()
+    launches_per_step = net.launch_count()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(k)
+    e1.record()
+    barrier()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI call: pinned host images in, host probabilities out ----
+    for w in range(3):
+        net.forward_host(host_in[w & 1], host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        net.forward_host(host_in[k & 1], host_out)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_s.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-layer CUDA-event profile (separate pass: events between kernels) -> dominant kernel + roofline ----
+    net.set_profiling(True)
+    nl = net.layer_count
+    acc = np.zeros(nl)
+    reps = max(3, min(args.steps, 10))
+    for k in range(reps):
+        net.forward(dev_in[k & 1], prob=prob)
+        torch.cuda.synchronize()
+        acc += np.array([net.layer_time_ms(l) for l in range(nl)])
+    net.set_profiling(False)
+    layer_ms = acc / reps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    names = {0: "conv1", 4: "conv2", 8: "conv3", 10: "conv4", 12: "conv5", 15: "fc6", 18: "fc7", 21: "fc8",
+             2: "lrn1+pool1", 6: "lrn2+pool2", 14: "pool5", 22: "softmax"}
+    per_layer = {}
+    for l in range(nl):
+        if layer_ms[l] <= 0:
+            continue
+        w = net.layer_work(l, B)
+        per_layer[names.get(l, "layer%d" % l)] = {
+            "ms": round(float(layer_ms[l]), 4), "alg_GBps": round(w["alg_bytes"] / (layer_ms[l] * 1e-3) / 1e9, 2),
+            "lookups_per_s": round(w["lookups"] / (layer_ms[l] * 1e-3), 1) if w["lookups"] else 0}
+    pq_layers = [l for l in ALEXNET_PQ if layer_ms[l] > 0]
+    dom = max(pq_layers, key=lambda l: layer_ms[l])
+    wd = net.layer_work(dom, B)
+    achieved = wd["alg_bytes"] / (layer_ms[dom] * 1e-3) / 1e9
+    sm_clk = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    gather_peak = 32.0 * ctx.sm_count * sm_clk * 1e6       # conflict-free 4-byte shared-memory lookups per second
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(names[dom])
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": wd["alg_bytes"], "ms_per_launch": round(float(layer_ms[dom]), 4),
+                "secondary_bound": {"resource": "shared-memory gather (32 lookups/clk/SM)",
+                                    "achieved_lookups_per_s": wd["lookups"] / (layer_ms[dom] * 1e-3),
+                                    "peak_lookups_per_s": gather_peak,
+                                    "frac": round(wd["lookups"] / (layer_ms[dom] * 1e-3) / gather_peak, 4)},
+                "note": "batched PQ layers are bound by on-chip LUT gather, not HBM (SURVEY.md 7.1); the HBM-bound "
+                        "kernel is the batch-1 FC assignment stream, reported in fc_b1"}
+
+    # ---- batch-1: latency and the HBM-bound FC assignment stream (L2 flushed between launches) ----
+    extra = {}
+    if rank == 0:
+        one = dev_in[0][:1].contiguous()
+        p1 = torch.empty((1, 1000), dtype=torch.float32, device=dev)
+        for w in range(5):
+            net.forward(one, prob=p1)
+        torch.cuda.synchronize()
+        lat = []
+        for k in range(30):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            net.forward(one, prob=p1)
+            b.record()
+            torch.cuda.synchronize()
+            lat.append(a.elapsed_time(b))
+        extra["latency_b1_ms"] = round(float(np.median(lat)), 4)
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        net.set_profiling(True)
+        fc_ms = {15: [], 18: [], 21: []}
+        for k in range(12):
+            flush.fill_(k & 0xFF)          # evict the 126 MB L2 so the assignment matrix streams from HBM
+            net.forward(one, prob=p1)
+            torch.cuda.synchronize()
+            if k >= 2:
+                for l in fc_ms:
+                    fc_ms[l].append(net.layer_time_ms(l))
+        net.set_profiling(False)
+        fc_b1 = {}
+        for l, v in fc_ms.items():
+            w = net.layer_work(l, 1)
+            ms = float(np.median(v))
+            fc_b1[names[l]] = {"ms": round(ms, 5), "alg_bytes": w["alg_bytes"],
+                               "achieved_GBps": round(w["alg_bytes"] / (ms * 1e-3) / 1e9, 1),
+                               "frac_of_hbm_peak": round(w["alg_bytes"] / (ms * 1e-3) / 1e9 / hbm_peak, 4)}
+        extra["fc_b1"] = fc_b1
+        del flush
+
+    # ---- the reference CPU path, single thread, same box, same run (rank 0, N = 1 only) ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        kind, med_ms, best_ms = cpu_reference_single_thread(dirpath, pfx, args.cpu_images)
+        cpu_baseline = {"value": 1000.0 / med_ms, "unit": "images/s", "cores": 1, "kind": kind,
+                        "sample": "%d images, batch 1, one pinned thread (median %.1f ms/img, best %.1f)"
+                                  % (args.cpu_images, med_ms, best_ms),
+                        "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": "alexnet_pq_forward_images_per_s", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, what, world),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * IMG_LEN * 4,
+                    "d2h_bytes_per_step": B * 1000 * 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "per_layer": per_layer,
+            "extra": extra, "impl": "b200",
+        }
+        print(json.dumps(line))
+    net.close()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-images", type=int, default=100, help="cpu_baseline sample size (images)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    q = importlib.import_module("quantized-cnn_b200")   # raises if libqcnn_b200.so is missing: no fallback
+    if args.impl == "reference":
+        return run_reference_arm(args, q)
+    return run_b200_arm(args, q)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,155 @@
+/*
+ * qcnn.h -- C ABI of the B200-native product-quantized (PQ) forward path.
+ *
+ * Drop-in boundary for the reference's CalcFeatMap_ConvAprx / CalcFeatMap_FCntAprx path
+ * (CAS-CLab/quantized-cnn, src/CaffeEva.cc).  The reference has no FFI of its own: the path sits behind
+ * private C++ members of class CaffeEva (include/CaffeEva.h:145-170).  Each entry point below names the
+ * reference member it replaces; INTEGRATION.md shows the binding a maintainer adds inside CaffeEva.cc.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on error with the text available from
+ *     qcnn_last_error() (thread-local).  No exceptions cross the boundary.
+ *   - pointers are DEVICE pointers unless the parameter name ends in _h (host).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); forward calls are asynchronous on it.
+ *   - activations are fp32; conv/pool/LRN maps are NHWC ([N][H][W][C]) exactly like the reference's featMapLst;
+ *     assignment indices are uint8, 0-based, "file order" as CaffePara::layerParaLst holds them after
+ *     LoadLayerPara (src/CaffePara.cc:239-306).
+ *   - one qcnn_ctx per GPU; a ctx and its layers are not thread-safe; distinct ctxs may be used concurrently.
+ *   - there is NO CPU fallback: every compute entry point fails with an error if no sm_100 device is usable.
+ */
+#ifndef QCNN_H_
+#define QCNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define QCNN_API __attribute__((visibility("default")))
+#else
+#define QCNN_API
+#endif
+
+typedef struct qcnn_ctx qcnn_ctx;
+typedef struct qcnn_layer qcnn_layer;
+typedef struct qcnn_net qcnn_net;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+QCNN_API const char* qcnn_version(void);
+QCNN_API const char* qcnn_last_error(void);
+QCNN_API int qcnn_ctx_create(int device, qcnn_ctx** out);
+QCNN_API void qcnn_ctx_destroy(qcnn_ctx* ctx);
+QCNN_API int qcnn_ctx_device(const qcnn_ctx* ctx);
+QCNN_API int qcnn_ctx_sm_count(const qcnn_ctx* ctx);
+
+/* ---- PQ layers (one-time set-up) ---------------------------------------------------------------------------
+ * Take the HOST arrays exactly as CaffePara::layerParaLst[l] holds them and do the re-layout + upload that
+ * CaffeEva::PrepCtrdBuf / PrepAsmtBuf (src/CaffeEva.cc:534-623) do on the CPU.
+ *   ctrd_h  [S][K][d]            f32   (ctrdLst, file order)
+ *   asmt_h  [Cout][k][k][S]      u8    (conv asmtLst)   |   [Dout][S] (FC asmtLst), 0-based, values < K
+ *   bias_h  [Cout] / [Dout]      f32
+ * Conv: ONE codebook is shared by all `grp` groups; group g reads input channels [g*Cin/grp, (g+1)*Cin/grp) and
+ * assignment columns [g*Cout/grp, ...) (src/CaffeEva.cc:795-811,847).  Subspace s covers the per-group channels
+ * [s*d, s*d + min(Cin/grp - s*d, d)) (src/CaffeEva.cc:1276-1277). */
+QCNN_API int qcnn_conv_layer_create(qcnn_ctx* ctx, int Cin, int Hin, int Win, int Cout, int ksz, int pad,
+                                    int stride, int grp, int S, int K, int d, const float* ctrd_h,
+                                    const uint8_t* asmt_h, const float* bias_h, qcnn_layer** out);
+QCNN_API int qcnn_fc_layer_create(qcnn_ctx* ctx, int Din, int Dout, int S, int K, int d, const float* ctrd_h,
+                                  const uint8_t* asmt_h, const float* bias_h, qcnn_layer** out);
+/* FC only: the source is an NHWC map [N][H][W][C] that the reference would first permute to NCHW
+ * (CaffeEva.cc:187-189, 236-238); fold that permute into the LUT stage's addressing (H*W*C must equal Din). */
+QCNN_API int qcnn_fc_layer_set_src_nhwc(qcnn_layer* layer, int H, int W, int C);
+/* Conv only: the source is NCHW [N][C][H][W] (the API input of CaffeEva::ExecForwardPass, CaffeEva.cc:225-228). */
+QCNN_API int qcnn_conv_layer_set_src_nchw(qcnn_layer* layer, int enable);
+/* tuning overrides for tests/benchmarks: "fc_nsplit" (subspace splits, 0 = automatic; 1 reproduces the reference's
+ * accumulation order exactly), "fc_tn" (images per CTA: 1, 4 or 8; 0 = automatic) */
+QCNN_API int qcnn_layer_set_param(qcnn_layer* layer, const char* name, int value);
+QCNN_API void qcnn_layer_destroy(qcnn_layer* layer);
+/* out[0..2] = Ho, Wo, Cout (FC: 1, 1, Dout) */
+QCNN_API int qcnn_layer_out_dims(const qcnn_layer* layer, int* out3);
+/* algorithmic HBM bytes of one forward launch at batch N and lookup-add / LUT MAC counts */
+QCNN_API int qcnn_layer_work(const qcnn_layer* layer, int N, double* alg_bytes, double* lookups, double* lut_macs);
+/* device copy of the re-laid-out assignment table, decoded back to plain 0-based indices in the reference's
+ * asmtBuf order ([kh][kw][S][Cout] / [S][Dout], CaffeEva.cc:585-586, 610-611) -- for bit-exact index tests */
+QCNN_API int qcnn_layer_read_asmt_h(const qcnn_layer* layer, uint8_t* out_h, size_t cap);
+
+/* ---- hot path -------------------------------------------------------------------------------------------- */
+/* replaces CaffeEva::CalcFeatMap_ConvAprx (src/CaffeEva.cc:760-868) incl. its GetInPdMat call (:810, :1261-1296)
+ * src [N][Hin][Win][Cin] -> dst [N][Ho][Wo][Cout]; fuse_relu != 0 additionally applies CalcFeatMap_ReLu (:1027). */
+QCNN_API int qcnn_conv_aprx_forward(qcnn_layer* layer, const float* src, int N, float* dst, int fuse_relu,
+                                    void* stream);
+/* replaces CaffeEva::CalcFeatMap_FCntAprx (src/CaffeEva.cc:968-1025); src [N][Din] -> dst [N][Dout] */
+QCNN_API int qcnn_fc_aprx_forward(qcnn_layer* layer, const float* src, int N, float* dst, int fuse_relu,
+                                  void* stream);
+
+/* ---- supporting layers (src/CaffeEva.cc:1027-1116, 870-921) ---------------------------------------------- */
+QCNN_API int qcnn_relu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, void* stream);
+QCNN_API int qcnn_lrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha,
+                      float beta, float k, void* stream);
+QCNN_API int qcnn_maxpool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int ksz,
+                          int pad, int stride, void* stream);
+/* LRN followed by max-pool in one pass (the reference always runs them back to back in AlexNet-family tables) */
+QCNN_API int qcnn_lrn_maxpool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int size,
+                              float alpha, float beta, float k, int ksz, int pad, int stride, void* stream);
+QCNN_API int qcnn_softmax(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, void* stream);
+QCNN_API int qcnn_nchw_to_nhwc(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, int H, int W,
+                               void* stream);
+QCNN_API int qcnn_nhwc_to_nchw(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C,
+                               void* stream);
+
+/* ---- whole network (CaffeEva::LoadCaffePara + ExecForwardPass, src/CaffeEva.cc:109-149, 213-261) ------------
+ * Layer table record == the reference's LayerInfo (include/CaffePara.h:28-41); type uses ENUM_LyrType order. */
+enum { QCNN_CONV = 0, QCNN_POOL = 1, QCNN_FCNT = 2, QCNN_RELU = 3, QCNN_LORN = 4, QCNN_DRPT = 5, QCNN_SMAX = 6 };
+typedef struct {
+  int type;
+  int padSiz, knlSiz, knlCnt, grpCnt, stride, nodCnt, lrnSiz;
+  float lrnAlp, lrnBet, lrnIni, drpRat;
+} qcnn_layer_info;
+
+/* model_name: "AlexNet" | "CaffeNet" | "VggCnnS" | "VGG16" | "CaffeNetFGB" | "CaffeNetFGD" (CaffeEva.cc:117-132);
+ * parameters are read from <dir>/<pfx>.{biasVec,ctrdLst}.NN.bin and <pfx>.asmtLst.NN.cbn (CaffePara.cc:262-281). */
+QCNN_API int qcnn_net_create(qcnn_ctx* ctx, const char* model_name, const char* dir, const char* pfx,
+                             qcnn_net** out);
+QCNN_API int qcnn_net_create_custom(qcnn_ctx* ctx, int layer_cnt, const qcnn_layer_info* layers, int img_chn,
+                                    int img_hei, int img_wid, const char* dir, const char* pfx, qcnn_net** out);
+QCNN_API void qcnn_net_destroy(qcnn_net* net);
+QCNN_API int qcnn_net_layer_count(const qcnn_net* net);
+QCNN_API int qcnn_net_out_len(const qcnn_net* net);
+/* keep != 0: every feature map featMapLst[0..layerCnt] is materialised un-fused (parity tests); default 0: ReLU is
+ * fused into the producing PQ kernel, LRN+pool are fused, dropout is elided. */
+QCNN_API int qcnn_net_set_keep_maps(qcnn_net* net, int keep);
+/* device-resident forward: img [N][C][H][W] (NCHW, as ExecForwardPass takes it) -> prob [N][out_len];
+ * logits (nullable) receives the input of the final softmax layer. */
+QCNN_API int qcnn_net_forward(qcnn_net* net, const float* img, int N, float* prob, float* logits, void* stream);
+/* host-buffer forward == CaffeEva::ExecForwardPass(imgDataIn, pProbVecOut): H2D, forward, D2H, synchronises. */
+QCNN_API int qcnn_net_forward_h(qcnn_net* net, const float* img_h, int N, float* prob_h, float* logits_h);
+/* images per pipeline chunk of qcnn_net_forward_h (default 64): H2D of chunk c+1 overlaps compute of chunk c */
+QCNN_API int qcnn_net_set_chunk(qcnn_net* net, int chunk);
+/* after a forward with keep_maps: device pointer + dims [N,H,W,C] of featMapLst[idx] */
+QCNN_API int qcnn_net_featmap(qcnn_net* net, int idx, const float** ptr, int* dims4);
+/* per-layer CUDA-event timing of the LAST forward (ms); enable before the forward.  Mirrors the reference's
+ * swIndvLayerLst stop-watches (CaffeEva.cc:192-194, 317-320). */
+QCNN_API int qcnn_net_set_profiling(qcnn_net* net, int enable);
+QCNN_API int qcnn_net_layer_time_ms(qcnn_net* net, int layer, float* ms);
+QCNN_API int qcnn_net_layer_work(qcnn_net* net, int layer, int N, double* alg_bytes, double* lookups,
+                                 double* lut_macs);
+/* number of kernels the last forward launched */
+QCNN_API int qcnn_net_launch_count(const qcnn_net* net);
+/* PQ layer handle of layer `l` (NULL for non-PQ layers); owned by the net */
+QCNN_API qcnn_layer* qcnn_net_pq_layer(qcnn_net* net, int l);
+
+/* ---- file formats (include/FileIO.h:56-178, 229-350), host only ------------------------------------------- */
+/* .bin: returns element count or -1; dims4 padded with 1; data_h may be NULL to query the shape */
+QCNN_API long qcnn_read_bin_f32(const char* path, int* dim_cnt, int* dims4, float* data_h, long cap);
+QCNN_API int qcnn_write_bin_f32(const char* path, int dim_cnt, const int* dims, const float* data_h);
+/* .cbn: 0-based indices as held after CaffePara::LoadLayerPara (reader's +1 and the loader's -1 both applied) */
+QCNN_API long qcnn_read_cbn_u8(const char* path, int* dim_cnt, int* dims4, int* bits, uint8_t* data_h, long cap);
+QCNN_API int qcnn_write_cbn_u8(const char* path, int dim_cnt, const int* dims, const uint8_t* idx0_h, int bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCNN_H_ */

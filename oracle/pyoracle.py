@@ -353,7 +353,10 @@ def synth_model(layers, in_chw, pq, seed=0, ctrd_std=0.05, bias_std=0.1):
 
 def synth_alexnet(seed=0):
     """AlexNet-shaped random model with He-style codebook scale so activations stay O(1..100) through 8 layers."""
-    return synth_model(alexnet_layers(), ALEXNET_IN, ALEXNET_PQ, seed=seed, ctrd_std=None, bias_std=0.05)
+    params = synth_model(alexnet_layers(), ALEXNET_IN, ALEXNET_PQ, seed=seed, ctrd_std=None, bias_std=0.05)
+    # keep the logits well inside expf's range: the reference softmax does not subtract the maximum (CaffeEva.cc:1107)
+    params[21]["ctrd"] = (params[21]["ctrd"] * np.float32(0.25)).astype(np.float32)
+    return params
 
 
 def save_model(dirpath, pfx, params):

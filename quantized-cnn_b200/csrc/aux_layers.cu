@@ -1,0 +1,222 @@
+// Supporting (non-PQ) layers of the forward pass, kept on the device so activations never bounce to the host.
+// They replace the remaining CalcFeatMap_* loop nests and the OpenVML / cblas elementwise calls they make
+// (reference src/CaffeEva.cc:870-921, 1027-1116; include/BlasWrapper.h:101-162).  All are HBM-streaming kernels:
+// NHWC maps, channel index fastest across lanes (coalesced), grid-stride loops sized to the SM count.
+#include "qcnn_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void relu_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  // CalcFeatMap_ReLu (CaffeEva.cc:1027-1036): max(0, x)
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = fmaxf(src[i], 0.0f);
+}
+
+// CalcFeatMap_LoRN (CaffeEva.cc:1038-1089), same operation order as the reference:
+//   t_c  = (x_c * x_c) * (alpha / size)                      vsSqr, cblas_sscal
+//   sum  = k; sum += t_{c-rad+w} for w = 0..size-1            vsAdd over the zero-padded window
+//   y_c  = x_c * expf(-beta * logf(sum))                      vsPowx_m fallback (BlasWrapper.h:134-147)
+__device__ __forceinline__ float LrnAt(const float* __restrict__ px, int c, int C, int size, int rad, float coeff,
+                                       float kini, float nbeta) {
+  float sum = kini;
+  for (int w = 0; w < size; w++) {
+    const int cc = c - rad + w;
+    float t = 0.0f;
+    if (cc >= 0 && cc < C) {
+      const float v = __ldg(px + cc);
+      t = __fmul_rn(__fmul_rn(v, v), coeff);
+    }
+    sum = __fadd_rn(sum, t);
+  }
+  return __fmul_rn(__ldg(px + c), expf(__fmul_rn(nbeta, logf(sum))));
+}
+
+__global__ void lrn_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t total, int C, int size,
+                           float coeff, float kini, float nbeta) {
+  const int rad = (size - 1) / 2;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t p = i / C;
+    const int c = static_cast<int>(i - p * C);
+    dst[i] = LrnAt(src + p * C, c, C, size, rad, coeff, kini, nbeta);
+  }
+}
+
+// CalcFeatMap_Pool (CaffeEva.cc:870-921): window clipped to the image, out = ceil((H+2p-k)/s)+1
+__global__ void maxpool_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int H, int W, int C,
+                               int Ho, int Wo, int ksz, int pad, int stride) {
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
+  const size_t gs = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int c = static_cast<int>(i % C);
+    size_t t = i / C;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    const int hL = max(0, ho * stride - pad), hU = min(H, ho * stride + ksz - pad) - 1;
+    const int wL = max(0, wo * stride - pad), wU = min(W, wo * stride + ksz - pad) - 1;
+    float m = -INFINITY;
+    for (int h = hL; h <= hU; h++)
+      for (int w = wL; w <= wU; w++)
+        m = fmaxf(m, __ldg(src + ((static_cast<size_t>(n) * H + h) * W + w) * C + c));
+    dst[i] = m;
+  }
+}
+
+// LRN immediately followed by max-pool (AlexNet / VggCnnS order): the normalised map is never written.
+__global__ void lrn_maxpool_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int H, int W, int C,
+                                   int Ho, int Wo, int size, float coeff, float kini, float nbeta, int ksz, int pad,
+                                   int stride) {
+  const int rad = (size - 1) / 2;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
+  const size_t gs = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int c = static_cast<int>(i % C);
+    size_t t = i / C;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    const int hL = max(0, ho * stride - pad), hU = min(H, ho * stride + ksz - pad) - 1;
+    const int wL = max(0, wo * stride - pad), wU = min(W, wo * stride + ksz - pad) - 1;
+    float m = -INFINITY;
+    for (int h = hL; h <= hU; h++)
+      for (int w = wL; w <= wU; w++)
+        m = fmaxf(m, LrnAt(src + ((static_cast<size_t>(n) * H + h) * W + w) * C, c, C, size, rad, coeff, kini, nbeta));
+    dst[i] = m;
+  }
+}
+
+// CalcFeatMap_SMax (CaffeEva.cc:1098-1116): y = exp(x) / sum(exp(x)), NO max subtraction (kept: parity).
+// One CTA per image; the float sum is reduced in a fixed tree order (deterministic).
+__global__ void softmax_kernel(const float* __restrict__ src, float* __restrict__ dst, int C) {
+  __shared__ float red[kThreads / 32];
+  __shared__ float total;
+  const float* x = src + static_cast<size_t>(blockIdx.x) * C;
+  float* y = dst + static_cast<size_t>(blockIdx.x) * C;
+  float part = 0.0f;
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    const float e = expf(x[c]);
+    y[c] = e;
+    part += e;
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int w = 0; w < kThreads / 32; w++) s += red[w];
+    total = s;
+  }
+  __syncthreads();
+  const float s = total;
+  for (int c = threadIdx.x; c < C; c += kThreads) y[c] = __fdiv_rn(y[c], s);
+}
+
+// Matrix::Permute(0,2,3,1) / (0,3,1,2) call sites (CaffeEva.cc:225-228, 236-238)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int C, int H, int W) {
+  const size_t total = static_cast<size_t>(N) * C * H * W;
+  const size_t gs = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += gs) {
+    // i indexes dst (NHWC)
+    const int c = static_cast<int>(i % C);
+    size_t t = i / C;
+    const int w = static_cast<int>(t % W); t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    dst[i] = __ldg(src + ((static_cast<size_t>(n) * C + c) * H + h) * W + w);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int H, int W, int C) {
+  const size_t total = static_cast<size_t>(N) * C * H * W;
+  const size_t gs = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += gs) {
+    // i indexes dst (NCHW)
+    const int w = static_cast<int>(i % W);
+    size_t t = i / W;
+    const int h = static_cast<int>(t % H); t /= H;
+    const int c = static_cast<int>(t % C);
+    const int n = static_cast<int>(t / C);
+    dst[i] = __ldg(src + ((static_cast<size_t>(n) * H + h) * W + w) * C + c);
+  }
+}
+
+int GridFor(const qcnn_ctx* ctx, size_t total) {
+  const size_t want = (total + kThreads - 1) / kThreads;
+  const size_t cap = static_cast<size_t>(ctx->sm_count) * 8;  // 8 CTAs of 256 threads per SM, grid-stride beyond
+  return static_cast<int>(std::max<size_t>(1, std::min(want, cap)));
+}
+
+}  // namespace
+
+namespace qcnn {
+
+int LaunchRelu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  relu_kernel<<<GridFor(ctx, n), kThreads, 0, st>>>(src, dst, n);
+  QCNN_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int LaunchLrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha, float beta,
+              float k, cudaStream_t st) {
+  QCNN_CHECK(C >= 1 && size >= 1, "qcnn_lrn: bad arguments");
+  const size_t total = pixels * C;
+  if (total == 0) return 0;
+  lrn_kernel<<<GridFor(ctx, total), kThreads, 0, st>>>(src, dst, total, C, size, alpha / size, k, -beta);
+  QCNN_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int LaunchMaxPool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int ksz, int pad,
+                  int stride, cudaStream_t st) {
+  QCNN_CHECK(N >= 1 && ksz >= 1 && stride >= 1, "qcnn_maxpool: bad arguments");
+  const int Ho = PoolOut(H, pad, ksz, stride), Wo = PoolOut(W, pad, ksz, stride);
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
+  maxpool_kernel<<<GridFor(ctx, total), kThreads, 0, st>>>(src, dst, N, H, W, C, Ho, Wo, ksz, pad, stride);
+  QCNN_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int LaunchLrnMaxPool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int size, float alpha,
+                     float beta, float k, int ksz, int pad, int stride, cudaStream_t st) {
+  QCNN_CHECK(N >= 1 && ksz >= 1 && stride >= 1 && size >= 1, "qcnn_lrn_maxpool: bad arguments");
+  const int Ho = PoolOut(H, pad, ksz, stride), Wo = PoolOut(W, pad, ksz, stride);
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
+  lrn_maxpool_kernel<<<GridFor(ctx, total), kThreads, 0, st>>>(src, dst, N, H, W, C, Ho, Wo, size, alpha / size, k,
+                                                               -beta, ksz, pad, stride);
+  QCNN_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int LaunchSoftmax(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, cudaStream_t st) {
+  QCNN_CHECK(N >= 1 && C >= 1, "qcnn_softmax: bad arguments");
+  softmax_kernel<<<N, kThreads, 0, st>>>(src, dst, C);
+  QCNN_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int LaunchNchwToNhwc(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, int H, int W, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(N) * C * H * W;
+  nchw_to_nhwc_kernel<<<GridFor(ctx, total), kThreads, 0, st>>>(src, dst, N, C, H, W);
+  QCNN_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int LaunchNhwcToNchw(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(N) * C * H * W;
+  nhwc_to_nchw_kernel<<<GridFor(ctx, total), kThreads, 0, st>>>(src, dst, N, H, W, C);
+  QCNN_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+}  // namespace qcnn

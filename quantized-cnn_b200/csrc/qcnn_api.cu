@@ -1,0 +1,365 @@
+// C-ABI entry points of libqcnn_b200.so (include/qcnn.h): context, PQ layer set-up (the device-side equivalent of
+// CaffeEva::PrepCtrdBuf / PrepAsmtBuf, reference src/CaffeEva.cc:534-623), per-layer forward calls, file formats.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../host/CaffePara.h"
+#include "../host/FileIO.h"
+#include "qcnn_internal.h"
+
+namespace qcnn {
+
+static thread_local char g_err[1024] = "";
+
+void SetError(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int CudaFail(cudaError_t e, const char* what, const char* file, int line) {
+  SetError("CUDA error %d (%s) at %s:%d: %s", static_cast<int>(e), cudaGetErrorString(e), file, line, what);
+  return 2;
+}
+
+}  // namespace qcnn
+
+using namespace qcnn;
+
+extern "C" {
+
+const char* qcnn_version(void) { return "qcnn-b200 0.1 (sm_100a)"; }
+const char* qcnn_last_error(void) { return g_err; }
+
+int qcnn_ctx_create(int device, qcnn_ctx** out) {
+  QCNN_CHECK(out != nullptr, "qcnn_ctx_create: out is NULL");
+  *out = nullptr;
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    SetError("qcnn_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return 2;
+  }
+  QCNN_CHECK(device >= 0 && device < cnt, "qcnn_ctx_create: device %d out of range (have %d)", device, cnt);
+  cudaDeviceProp prop;
+  QCNN_CUDA(cudaGetDeviceProperties(&prop, device));
+  QCNN_CHECK(prop.major == 10, "qcnn_ctx_create: device %d is sm_%d%d; this build carries sm_100a code only", device,
+             prop.major, prop.minor);
+  QCNN_CUDA(cudaSetDevice(device));
+  qcnn_ctx* ctx = new qcnn_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  ctx->launches = 0;
+  *out = ctx;
+  return 0;
+}
+
+void qcnn_ctx_destroy(qcnn_ctx* ctx) { delete ctx; }
+int qcnn_ctx_device(const qcnn_ctx* ctx) { return ctx ? ctx->device : -1; }
+int qcnn_ctx_sm_count(const qcnn_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+static qcnn_layer* NewLayer(qcnn_ctx* ctx, int kind) {
+  qcnn_layer* L = new qcnn_layer();
+  memset(static_cast<void*>(L), 0, sizeof(*L));
+  L->ctx = ctx;
+  L->kind = kind;
+  return L;
+}
+
+static int CheckPq(const char* who, int S, int K, int d, const uint8_t* asmt, size_t n) {
+  QCNN_CHECK(S >= 1 && d >= 1, "%s: S and d must be >= 1", who);
+  QCNN_CHECK(K >= 1 && K <= 256, "%s: K=%d does not fit uint8 assignments", who, K);
+  for (size_t i = 0; i < n; i++) {
+    if (asmt[i] >= K) {
+      SetError("%s: assignment[%zu]=%d is not < K=%d", who, i, static_cast<int>(asmt[i]), K);
+      return 1;
+    }
+  }
+  return 0;
+}
+
+int qcnn_conv_layer_create(qcnn_ctx* ctx, int Cin, int Hin, int Win, int Cout, int ksz, int pad, int stride, int grp,
+                           int S, int K, int d, const float* ctrd_h, const uint8_t* asmt_h, const float* bias_h,
+                           qcnn_layer** out) {
+  QCNN_CHECK(ctx && out && ctrd_h && asmt_h && bias_h, "qcnn_conv_layer_create: NULL argument");
+  *out = nullptr;
+  QCNN_CHECK(grp >= 1 && Cin % grp == 0 && Cout % grp == 0, "qcnn_conv_layer_create: channels not divisible by grp");
+  QCNN_CHECK(ksz >= 1 && stride >= 1 && pad >= 0 && pad < ksz, "qcnn_conv_layer_create: bad kernel geometry");
+  QCNN_CHECK(Hin + 2 * pad >= ksz && Win + 2 * pad >= ksz, "qcnn_conv_layer_create: kernel larger than input");
+  const int taps = ksz * ksz;
+  if (int rc = CheckPq("qcnn_conv_layer_create", S, K, d, asmt_h, static_cast<size_t>(Cout) * taps * S)) return rc;
+  QCNN_CUDA(cudaSetDevice(ctx->device));
+  qcnn_layer* L = NewLayer(ctx, QCNN_KIND_CONV);
+  L->Cin = Cin; L->Hin = Hin; L->Win = Win; L->Cout = Cout; L->ksz = ksz; L->pad = pad; L->stride = stride;
+  L->grp = grp; L->S = S; L->K = K; L->d = d;
+  L->Ho = (Hin + 2 * pad - ksz) / stride + 1;  // reference CaffeEva.cc:361-362
+  L->Wo = (Win + 2 * pad - ksz) / stride + 1;
+  const int Kg = Cout / grp, KgPad = RoundUp(Kg, 16);
+  // assignments: file order [Cout][kh][kw][S] -> device [grp][S][tap][KgPad]
+  // (the reference's asmtBuf is [kh][kw][S][Cout], CaffeEva.cc:585-586; we additionally make the subspace the
+  //  slow index because the fused kernel walks s in its outer loop)
+  std::vector<uint8_t> dev(static_cast<size_t>(grp) * S * taps * KgPad, 0);
+  for (int g = 0; g < grp; g++)
+    for (int c = 0; c < Kg; c++)
+      for (int t = 0; t < taps; t++)
+        for (int s = 0; s < S; s++)
+          dev[((static_cast<size_t>(g) * S + s) * taps + t) * KgPad + c] =
+              asmt_h[((static_cast<size_t>(g) * Kg + c) * taps + t) * S + s];
+  L->asmt_bytes = dev.size();
+  int rc = 0;
+  do {
+    if ((rc = (cudaMalloc(&L->d_asmt, dev.size()) != cudaSuccess))) break;
+    if ((rc = (cudaMalloc(&L->d_ctrd, sizeof(float) * S * K * d) != cudaSuccess))) break;
+    if ((rc = (cudaMalloc(&L->d_bias, sizeof(float) * Cout) != cudaSuccess))) break;
+    if ((rc = (cudaMemcpy(L->d_asmt, dev.data(), dev.size(), cudaMemcpyHostToDevice) != cudaSuccess))) break;
+    if ((rc = (cudaMemcpy(L->d_ctrd, ctrd_h, sizeof(float) * S * K * d, cudaMemcpyHostToDevice) != cudaSuccess))) break;
+    if ((rc = (cudaMemcpy(L->d_bias, bias_h, sizeof(float) * Cout, cudaMemcpyHostToDevice) != cudaSuccess))) break;
+  } while (0);
+  if (rc) {
+    CudaFail(cudaGetLastError(), "conv layer upload", __FILE__, __LINE__);
+    qcnn_layer_destroy(L);
+    return 2;
+  }
+  if (PlanConv(L, 256)) {  // validates that a tiling exists; re-planned per batch size at launch
+    qcnn_layer_destroy(L);
+    return 1;
+  }
+  *out = L;
+  return 0;
+}
+
+int qcnn_fc_layer_create(qcnn_ctx* ctx, int Din, int Dout, int S, int K, int d, const float* ctrd_h,
+                         const uint8_t* asmt_h, const float* bias_h, qcnn_layer** out) {
+  QCNN_CHECK(ctx && out && ctrd_h && asmt_h && bias_h, "qcnn_fc_layer_create: NULL argument");
+  *out = nullptr;
+  QCNN_CHECK(Din >= 1 && Dout >= 1, "qcnn_fc_layer_create: bad dimensions");
+  if (int rc = CheckPq("qcnn_fc_layer_create", S, K, d, asmt_h, static_cast<size_t>(Dout) * S)) return rc;
+  QCNN_CHECK(K == 16 || K == 32 || K == 64 || K == 128 || K == 256,
+             "qcnn_fc_layer_create: unsupported codebook size K=%d (supported: 16, 32, 64, 128, 256)", K);
+  QCNN_CUDA(cudaSetDevice(ctx->device));
+  qcnn_layer* L = NewLayer(ctx, QCNN_KIND_FC);
+  L->Din = Din; L->Dout = Dout; L->S = S; L->K = K; L->d = d;
+  L->Ho = 1; L->Wo = 1; L->Cout = Dout;
+  L->DoutPad = RoundUp(Dout, 16);
+  L->kshift = (K <= 64) ? 2 : 0;
+  // assignments: file order [Dout][S] -> device [S][DoutPad] (reference asmtBuf [S][Dout], CaffeEva.cc:610-611),
+  // stored as byte offsets into a LUT row (idx * 4) when that fits a byte
+  std::vector<uint8_t> dev(static_cast<size_t>(S) * L->DoutPad, 0);
+  for (int o = 0; o < Dout; o++)
+    for (int s = 0; s < S; s++)
+      dev[static_cast<size_t>(s) * L->DoutPad + o] = static_cast<uint8_t>(asmt_h[static_cast<size_t>(o) * S + s] << L->kshift);
+  L->asmt_bytes = dev.size();
+  int rc = 0;
+  do {
+    if ((rc = (cudaMalloc(&L->d_asmt, dev.size()) != cudaSuccess))) break;
+    if ((rc = (cudaMalloc(&L->d_ctrd, sizeof(float) * S * K * d) != cudaSuccess))) break;
+    if ((rc = (cudaMalloc(&L->d_bias, sizeof(float) * Dout) != cudaSuccess))) break;
+    if ((rc = (cudaMemcpy(L->d_asmt, dev.data(), dev.size(), cudaMemcpyHostToDevice) != cudaSuccess))) break;
+    if ((rc = (cudaMemcpy(L->d_ctrd, ctrd_h, sizeof(float) * S * K * d, cudaMemcpyHostToDevice) != cudaSuccess))) break;
+    if ((rc = (cudaMemcpy(L->d_bias, bias_h, sizeof(float) * Dout, cudaMemcpyHostToDevice) != cudaSuccess))) break;
+  } while (0);
+  if (rc) {
+    CudaFail(cudaGetLastError(), "fc layer upload", __FILE__, __LINE__);
+    qcnn_layer_destroy(L);
+    return 2;
+  }
+  *out = L;
+  return 0;
+}
+
+int qcnn_fc_layer_set_src_nhwc(qcnn_layer* L, int H, int W, int C) {
+  QCNN_CHECK(L && L->kind == QCNN_KIND_FC, "qcnn_fc_layer_set_src_nhwc: not an FC layer");
+  if (H == 0 && W == 0 && C == 0) { L->src_h = L->src_w = L->src_c = 0; return 0; }
+  QCNN_CHECK(H >= 1 && W >= 1 && C >= 1 && H * W * C == L->Din, "qcnn_fc_layer_set_src_nhwc: H*W*C=%d != Din=%d",
+             H * W * C, L->Din);
+  L->src_h = H; L->src_w = W; L->src_c = C;
+  return 0;
+}
+
+int qcnn_conv_layer_set_src_nchw(qcnn_layer* L, int enable) {
+  QCNN_CHECK(L && L->kind == QCNN_KIND_CONV, "qcnn_conv_layer_set_src_nchw: not a conv layer");
+  QCNN_CHECK(!enable || L->stride > 1, "qcnn_conv_layer_set_src_nchw: only the strided kernel reads NCHW");
+  L->src_nchw = enable ? 1 : 0;
+  return 0;
+}
+
+int qcnn_layer_set_param(qcnn_layer* L, const char* name, int value) {
+  QCNN_CHECK(L && name, "qcnn_layer_set_param: NULL argument");
+  if (!strcmp(name, "fc_nsplit")) L->opt_fc_nsplit = value;
+  else if (!strcmp(name, "fc_tn")) L->opt_fc_tn = value;
+  else { SetError("qcnn_layer_set_param: unknown parameter '%s'", name); return 1; }
+  return 0;
+}
+
+void qcnn_layer_destroy(qcnn_layer* L) {
+  if (!L) return;
+  if (L->d_asmt) cudaFree(L->d_asmt);
+  if (L->d_ctrd) cudaFree(L->d_ctrd);
+  if (L->d_bias) cudaFree(L->d_bias);
+  if (L->d_partial) cudaFree(L->d_partial);
+  delete L;
+}
+
+int qcnn_layer_out_dims(const qcnn_layer* L, int* out3) {
+  QCNN_CHECK(L && out3, "qcnn_layer_out_dims: NULL argument");
+  out3[0] = L->Ho; out3[1] = L->Wo; out3[2] = L->Cout;
+  return 0;
+}
+
+// conv 4*N*Hi*Wi*Cin + 4*N*Ho*Wo*Cout + k^2*S*Cout + 4*S*K*d + 4*Cout ;
+//                 FC   4*N*Din + 4*N*Dout + S*Dout + 4*S*K*d + 4*Dout
+int qcnn_layer_work(const qcnn_layer* L, int N, double* alg_bytes, double* lookups, double* lut_macs) {
+  QCNN_CHECK(L, "qcnn_layer_work: NULL layer");
+  double bytes, lk, macs;
+  if (L->kind == QCNN_KIND_CONV) {
+    const double taps = static_cast<double>(L->ksz) * L->ksz;
+    bytes = 4.0 * N * L->Hin * L->Win * L->Cin + 4.0 * N * L->Ho * L->Wo * L->Cout + taps * L->S * L->Cout +
+            4.0 * L->S * L->K * L->d + 4.0 * L->Cout;
+    // valid (in-bounds) taps only, as the reference counts them
+    double vt = 0;
+    for (int ho = 0; ho < L->Ho; ho++) {
+      const int hL = ho * L->stride - L->pad;
+      const int nh = std::min(L->ksz - 1, L->Hin - 1 - hL) - std::max(0, -hL) + 1;
+      for (int wo = 0; wo < L->Wo; wo++) {
+        const int wL = wo * L->stride - L->pad;
+        const int nw = std::min(L->ksz - 1, L->Win - 1 - wL) - std::max(0, -wL) + 1;
+        vt += static_cast<double>(nh) * nw;
+      }
+    }
+    lk = vt * L->S * L->Cout * N;
+    const int Cg = L->Cin / L->grp;
+    double dims = 0;
+    for (int s = 0; s < L->S; s++) dims += std::max(0, std::min(Cg - s * L->d, L->d));
+    macs = static_cast<double>(N) * L->Hin * L->Win * L->grp * dims * L->K;
+  } else {
+    bytes = 4.0 * N * L->Din + 4.0 * N * L->Dout + static_cast<double>(L->S) * L->Dout + 4.0 * L->S * L->K * L->d +
+            4.0 * L->Dout;
+    lk = static_cast<double>(N) * L->S * L->Dout;
+    double dims = 0;
+    for (int s = 0; s < L->S; s++) dims += std::max(0, std::min(L->Din - s * L->d, L->d));
+    macs = static_cast<double>(N) * dims * L->K;
+  }
+  if (alg_bytes) *alg_bytes = bytes;
+  if (lookups) *lookups = lk;
+  if (lut_macs) *lut_macs = macs;
+  return 0;
+}
+
+int qcnn_layer_read_asmt_h(const qcnn_layer* L, uint8_t* out_h, size_t cap) {
+  QCNN_CHECK(L && out_h, "qcnn_layer_read_asmt_h: NULL argument");
+  std::vector<uint8_t> dev(L->asmt_bytes);
+  QCNN_CUDA(cudaMemcpy(dev.data(), L->d_asmt, dev.size(), cudaMemcpyDeviceToHost));
+  if (L->kind == QCNN_KIND_CONV) {
+    const int taps = L->ksz * L->ksz, Kg = L->Cout / L->grp, KgPad = RoundUp(Kg, 16);
+    QCNN_CHECK(cap >= static_cast<size_t>(taps) * L->S * L->Cout, "qcnn_layer_read_asmt_h: buffer too small");
+    for (int t = 0; t < taps; t++)
+      for (int s = 0; s < L->S; s++)
+        for (int c = 0; c < L->Cout; c++) {
+          const int g = c / Kg, cl = c % Kg;
+          out_h[(static_cast<size_t>(t) * L->S + s) * L->Cout + c] =
+              dev[((static_cast<size_t>(g) * L->S + s) * taps + t) * KgPad + cl];
+        }
+  } else {
+    QCNN_CHECK(cap >= static_cast<size_t>(L->S) * L->Dout, "qcnn_layer_read_asmt_h: buffer too small");
+    for (int s = 0; s < L->S; s++)
+      for (int o = 0; o < L->Dout; o++)
+        out_h[static_cast<size_t>(s) * L->Dout + o] = dev[static_cast<size_t>(s) * L->DoutPad + o] >> L->kshift;
+  }
+  return 0;
+}
+
+int qcnn_conv_aprx_forward(qcnn_layer* L, const float* src, int N, float* dst, int fuse_relu, void* stream) {
+  QCNN_CHECK(L && src && dst, "qcnn_conv_aprx_forward: NULL argument");
+  return LaunchConv(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
+}
+
+int qcnn_fc_aprx_forward(qcnn_layer* L, const float* src, int N, float* dst, int fuse_relu, void* stream) {
+  QCNN_CHECK(L && src && dst, "qcnn_fc_aprx_forward: NULL argument");
+  return LaunchFc(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
+}
+
+int qcnn_relu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, void* stream) {
+  QCNN_CHECK(ctx && src && dst, "qcnn_relu: NULL argument");
+  return LaunchRelu(ctx, src, dst, n, static_cast<cudaStream_t>(stream));
+}
+int qcnn_lrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha, float beta,
+             float k, void* stream) {
+  QCNN_CHECK(ctx && src && dst, "qcnn_lrn: NULL argument");
+  return LaunchLrn(ctx, src, dst, pixels, C, size, alpha, beta, k, static_cast<cudaStream_t>(stream));
+}
+int qcnn_maxpool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int ksz, int pad, int stride,
+                 void* stream) {
+  QCNN_CHECK(ctx && src && dst, "qcnn_maxpool: NULL argument");
+  return LaunchMaxPool(ctx, src, dst, N, H, W, C, ksz, pad, stride, static_cast<cudaStream_t>(stream));
+}
+int qcnn_lrn_maxpool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int size, float alpha,
+                     float beta, float k, int ksz, int pad, int stride, void* stream) {
+  QCNN_CHECK(ctx && src && dst, "qcnn_lrn_maxpool: NULL argument");
+  return LaunchLrnMaxPool(ctx, src, dst, N, H, W, C, size, alpha, beta, k, ksz, pad, stride,
+                          static_cast<cudaStream_t>(stream));
+}
+int qcnn_softmax(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, void* stream) {
+  QCNN_CHECK(ctx && src && dst, "qcnn_softmax: NULL argument");
+  return LaunchSoftmax(ctx, src, dst, N, C, static_cast<cudaStream_t>(stream));
+}
+int qcnn_nchw_to_nhwc(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, int H, int W, void* stream) {
+  QCNN_CHECK(ctx && src && dst, "qcnn_nchw_to_nhwc: NULL argument");
+  return LaunchNchwToNhwc(ctx, src, dst, N, C, H, W, static_cast<cudaStream_t>(stream));
+}
+int qcnn_nhwc_to_nchw(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, void* stream) {
+  QCNN_CHECK(ctx && src && dst, "qcnn_nhwc_to_nchw: NULL argument");
+  return LaunchNhwcToNchw(ctx, src, dst, N, H, W, C, static_cast<cudaStream_t>(stream));
+}
+
+// ---- file formats (host) ---------------------------------------------------------------------------------
+long qcnn_read_bin_f32(const char* path, int* dim_cnt, int* dims4, float* data_h, long cap) {
+  Matrix<float> m;
+  if (!path || !FileIO::ReadBinFile(path, &m)) { SetError("qcnn_read_bin_f32: cannot read %s", path ? path : "(null)"); return -1; }
+  if (dim_cnt) *dim_cnt = m.GetDimCnt();
+  if (dims4) for (int i = 0; i < 4; i++) dims4[i] = m.GetDimLen(i);
+  const long n = m.GetEleCnt();
+  if (data_h) memcpy(data_h, m.GetDataPtr(), sizeof(float) * std::min(n, cap));
+  return n;
+}
+
+int qcnn_write_bin_f32(const char* path, int dim_cnt, const int* dims, const float* data_h) {
+  QCNN_CHECK(path && dims && data_h && dim_cnt >= 1 && dim_cnt <= 4, "qcnn_write_bin_f32: bad argument");
+  Matrix<float> m(dim_cnt, dims);
+  memcpy(m.GetDataPtr(), data_h, sizeof(float) * m.GetEleCnt());
+  QCNN_CHECK(FileIO::WriteBinFile(path, m), "qcnn_write_bin_f32: cannot write %s", path);
+  return 0;
+}
+
+long qcnn_read_cbn_u8(const char* path, int* dim_cnt, int* dims4, int* bits, uint8_t* data_h, long cap) {
+  Matrix<uint8_t> m;
+  if (!path || !FileIO::ReadCbnFile(path, &m)) { SetError("qcnn_read_cbn_u8: cannot read %s", path ? path : "(null)"); return -1; }
+  if (dim_cnt) *dim_cnt = m.GetDimCnt();
+  if (dims4) for (int i = 0; i < 4; i++) dims4[i] = m.GetDimLen(i);
+  if (bits) *bits = FileIO::PeekCbnBits(path);
+  const long n = m.GetEleCnt();
+  if (data_h) {
+    const uint8_t* p = m.GetDataPtr();
+    for (long i = 0; i < std::min(n, cap); i++) data_h[i] = static_cast<uint8_t>(p[i] - 1);  // CaffePara.cc:285-288
+  }
+  return n;
+}
+
+int qcnn_write_cbn_u8(const char* path, int dim_cnt, const int* dims, const uint8_t* idx0_h, int bits) {
+  QCNN_CHECK(path && dims && idx0_h && dim_cnt >= 1 && dim_cnt <= 4, "qcnn_write_cbn_u8: bad argument");
+  Matrix<uint8_t> m(dim_cnt, dims);
+  uint8_t* p = m.GetDataPtr();
+  for (int i = 0, n = m.GetEleCnt(); i < n; i++) p[i] = static_cast<uint8_t>(idx0_h[i] + 1);  // writer takes 1-based
+  QCNN_CHECK(FileIO::WriteCbnFile(path, m, bits), "qcnn_write_cbn_u8: cannot write %s", path);
+  return 0;
+}
+
+}  // extern "C"

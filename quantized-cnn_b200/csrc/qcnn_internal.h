@@ -1,0 +1,142 @@
+// Internal declarations shared by the .cu / .cc files of libqcnn_b200.so (not part of the C ABI).
+#ifndef QCNN_INTERNAL_H_
+#define QCNN_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/qcnn.h"
+
+namespace qcnn {
+
+// thread-local error text behind qcnn_last_error()
+void SetError(const char* fmt, ...);
+int CudaFail(cudaError_t e, const char* what, const char* file, int line);
+
+#define QCNN_CUDA(call)                                                      \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) return ::qcnn::CudaFail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define QCNN_CHECK(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::qcnn::SetError(__VA_ARGS__);     \
+      return 1;                          \
+    }                                    \
+  } while (0)
+
+inline int CeilDiv(int a, int b) { return (a + b - 1) / b; }
+inline int RoundUp(int a, int b) { return CeilDiv(a, b) * b; }
+
+}  // namespace qcnn
+
+struct qcnn_ctx {
+  int device;
+  int sm_count;
+  int cc_major, cc_minor;
+  size_t smem_optin;  // max dynamic shared memory per block (opt-in)
+  unsigned long long launches;  // kernels launched through this ctx (monotonic)
+};
+
+enum { QCNN_KIND_CONV = 0, QCNN_KIND_FC = 1 };
+
+// ---- kernel argument blocks --------------------------------------------------------------------------------
+struct FcArgs {
+  const float* src;
+  float* dst;
+  float* partial;      // [nsplit][N][DoutPad] when nsplit > 1
+  const float* ctrd;   // [S][K][d] (file order)
+  const uint8_t* asmt; // [S][DoutPad], value = idx << kshift
+  const float* bias;
+  int N, Din, Dout, DoutPad, S, K, d;
+  int hw, ch;          // source is NHWC [hw][ch] per image (hw == 0: flat)
+  int s_per_split, nsplit;
+  int relu;
+};
+
+struct ConvArgs {
+  const float* src;
+  float* dst;
+  const float* ctrd;    // [S][K][d] (file order), shared by all groups
+  const uint8_t* asmt;  // [G][S][taps][KgPad]
+  const float* bias;
+  int N, Hi, Wi, Cin, Ho, Wo, Cout, ksz, pad, stride, G, Cg, Kg, KgPad, S, K, d;
+  int src_nchw;
+  // tiling plan
+  int R, nstrips;       // output rows per CTA / strips per image
+  int PW;               // s1: row pitch of the flat padded grid; roll: phase length PH
+  int RI;               // s1: input rows held per strip
+  int PP;               // LUT pitch in floats (positions per codeword row), multiple of 4
+  int CT, nct;          // output channels per CTA (per group) / channel tiles per group
+  int pwarps, cwarps, rgroups;
+  int ksplit;           // LUT build: K is split over ksplit thread groups
+  int relu;
+};
+
+struct ConvPlan {
+  int kernel;           // 0 = stride-1 flat kernel, 1 = rolling-row kernel
+  int CPT, J;
+  int threads;
+  size_t smem;
+  ConvArgs a;           // geometry + tiling (pointers/N filled at launch)
+};
+
+struct qcnn_layer {
+  qcnn_ctx* ctx;
+  int kind;
+  // geometry
+  int Cin, Hin, Win, Cout, ksz, pad, stride, grp, S, K, d;
+  int Ho, Wo;
+  int Din, Dout, DoutPad;
+  // FC source permutation (NHWC map) / conv NCHW source
+  int src_h, src_w, src_c;
+  int src_nchw;
+  // device parameters
+  float* d_ctrd;
+  uint8_t* d_asmt;
+  float* d_bias;
+  size_t asmt_bytes;
+  int kshift;           // FC: stored assignment = idx << kshift
+  // plans
+  ConvPlan plan;
+  int plan_N;            // batch size the cached plan was made for (0 = none)
+  // FC scratch
+  float* d_partial;
+  size_t partial_bytes;
+  // tuning overrides (0 = automatic)
+  int opt_fc_nsplit;
+  int opt_fc_tn;
+};
+
+namespace qcnn {
+
+int PlanConv(qcnn_layer* L, int N);
+int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st);
+int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st);
+
+int LaunchRelu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, cudaStream_t st);
+int LaunchLrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha, float beta,
+              float k, cudaStream_t st);
+int LaunchMaxPool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int ksz, int pad,
+                  int stride, cudaStream_t st);
+int LaunchLrnMaxPool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int size, float alpha,
+                     float beta, float k, int ksz, int pad, int stride, cudaStream_t st);
+int LaunchSoftmax(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, cudaStream_t st);
+int LaunchNchwToNhwc(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, int H, int W, cudaStream_t st);
+int LaunchNhwcToNchw(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, cudaStream_t st);
+
+inline int PoolOut(int in, int pad, int ksz, int stride) {
+  // ceil((in + 2p - k) / s) + 1   (reference src/CaffeEva.cc:365-372)
+  int num = in + 2 * pad - ksz;
+  int q = num >= 0 ? (num + stride - 1) / stride : -((-num) / stride);
+  return q + 1;
+}
+
+}  // namespace qcnn
+
+#endif  // QCNN_INTERNAL_H_

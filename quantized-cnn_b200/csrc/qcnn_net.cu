@@ -1,0 +1,459 @@
+// Whole-network executor on the device: the layer loop of CaffeEva::ExecForwardPass (reference
+// src/CaffeEva.cc:213-261) + CaffeEva::LoadCaffePara (:109-149) with every feature map resident in HBM.
+// Differences from the reference executor, none of which change results beyond fp32 rounding:
+//   * runtime batch size (the reference hard-codes kDataCntInBatch = 1, CaffeEva.cc:23);
+//   * NCHW->NHWC of the input is folded into the first conv's loads when that conv runs the strided kernel,
+//     NHWC->NCHW before the first FC layer is folded into that layer's LUT addressing (never materialised);
+//   * ReLU is fused into the producing PQ kernel, LRN+pool into one pass, dropout (identity at test time,
+//     CaffeEva.cc:1091-1096) is elided by aliasing -- unless keep_maps asks for the un-fused featMapLst.
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../host/CaffePara.h"
+#include "qcnn_internal.h"
+
+using namespace qcnn;
+
+struct NetLayer {
+  qcnn_layer_info info;
+  qcnn_layer* pq;
+  int Hin, Win, Cin;     // NHWC dims of featMapLst[l]
+  int Hout, Wout, Cout;  // NHWC dims of featMapLst[l+1]
+};
+
+struct qcnn_net {
+  qcnn_ctx* ctx;
+  std::vector<NetLayer> layers;
+  int imgC, imgH, imgW;
+  int keep;
+  int profiling;
+  int capN;
+  std::vector<float*> maps;  // device buffers for featMapLst[0..L]; maps[0] only used when the input must be permuted
+  std::vector<const float*> mapPtr;  // where featMapLst[i] of the last forward actually lives (NULL if fused away)
+  std::vector<cudaEvent_t> evBeg, evEnd;
+  std::vector<char> evUsed;
+  unsigned long long lastLaunches;
+  // host-buffer forward: double-buffered input chunks + output staging
+  float* d_in[2];
+  size_t d_in_cap;
+  float* d_prob;
+  float* d_logit;
+  size_t d_out_cap;
+  cudaStream_t stCopy, stComp;
+  cudaEvent_t evH2D[2], evDone[2];
+  int chunk;
+};
+
+static size_t MapElems(const NetLayer& L) { return static_cast<size_t>(L.Hout) * L.Wout * L.Cout; }
+
+static void FreeMaps(qcnn_net* net) {
+  for (float*& p : net->maps) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+  net->capN = 0;
+}
+
+static int EnsureCapacity(qcnn_net* net, int N) {
+  if (N <= net->capN) return 0;
+  FreeMaps(net);
+  const size_t L = net->layers.size();
+  net->maps.assign(L + 1, nullptr);
+  QCNN_CUDA(cudaMalloc(&net->maps[0], sizeof(float) * N * net->imgC * net->imgH * net->imgW));
+  for (size_t l = 0; l < L; l++) QCNN_CUDA(cudaMalloc(&net->maps[l + 1], sizeof(float) * N * MapElems(net->layers[l])));
+  net->capN = N;
+  return 0;
+}
+
+static int BuildNet(qcnn_ctx* ctx, CaffePara& para, qcnn_net** out) {
+  qcnn_net* net = new qcnn_net();
+  net->ctx = ctx;
+  net->imgC = para.imgChnIn; net->imgH = para.imgHeiIn; net->imgW = para.imgWidIn;
+  net->keep = 0; net->profiling = 0; net->capN = 0; net->lastLaunches = 0;
+  net->d_in[0] = net->d_in[1] = nullptr; net->d_in_cap = 0;
+  net->d_prob = net->d_logit = nullptr; net->d_out_cap = 0;
+  net->stCopy = net->stComp = nullptr;
+  net->chunk = 64;
+  int H = para.imgHeiIn, W = para.imgWidIn, C = para.imgChnIn;
+  bool seenFc = false;
+  int rc = 0;
+  for (int l = 0; l < para.layerCnt && rc == 0; l++) {
+    const LayerInfo& li = para.layerInfoLst[l];
+    NetLayer nl;
+    memset(&nl, 0, sizeof(nl));
+    nl.info.type = static_cast<int>(li.type);
+    nl.info.padSiz = li.padSiz; nl.info.knlSiz = li.knlSiz; nl.info.knlCnt = li.knlCnt; nl.info.grpCnt = li.grpCnt;
+    nl.info.stride = li.stride; nl.info.nodCnt = li.nodCnt; nl.info.lrnSiz = li.lrnSiz; nl.info.lrnAlp = li.lrnAlp;
+    nl.info.lrnBet = li.lrnBet; nl.info.lrnIni = li.lrnIni; nl.info.drpRat = li.drpRat;
+    nl.Hin = H; nl.Win = W; nl.Cin = C;
+    const LayerPara& lp = para.layerParaLst[l];
+    switch (li.type) {
+      case ENUM_LyrType::Conv: {
+        if (lp.ctrdLst.GetDimCnt() != 3 || lp.asmtLst.GetDimCnt() != 4) {
+          SetError("layer %d: conv parameters have unexpected rank", l + 1);
+          rc = 1;
+          break;
+        }
+        const int S = lp.ctrdLst.GetDimLen(0), K = lp.ctrdLst.GetDimLen(1), d = lp.ctrdLst.GetDimLen(2);
+        if (lp.asmtLst.GetDimLen(0) != li.knlCnt || lp.asmtLst.GetDimLen(1) != li.knlSiz ||
+            lp.asmtLst.GetDimLen(2) != li.knlSiz || lp.asmtLst.GetDimLen(3) != S ||
+            lp.biasVec.GetEleCnt() != li.knlCnt) {
+          SetError("layer %d: conv parameter shapes do not match the layer table", l + 1);
+          rc = 1;
+          break;
+        }
+        rc = qcnn_conv_layer_create(ctx, C, H, W, li.knlCnt, li.knlSiz, li.padSiz, li.stride, li.grpCnt, S, K, d,
+                                    lp.ctrdLst.GetDataPtr(), lp.asmtLst.GetDataPtr(), lp.biasVec.GetDataPtr(), &nl.pq);
+        if (rc) break;
+        H = nl.pq->Ho; W = nl.pq->Wo; C = li.knlCnt;
+        break;
+      }
+      case ENUM_LyrType::FCnt: {
+        if (lp.ctrdLst.GetDimCnt() != 3 || lp.asmtLst.GetDimCnt() != 2) {
+          SetError("layer %d: FC parameters have unexpected rank", l + 1);
+          rc = 1;
+          break;
+        }
+        const int S = lp.ctrdLst.GetDimLen(0), K = lp.ctrdLst.GetDimLen(1), d = lp.ctrdLst.GetDimLen(2);
+        const int Din = H * W * C;
+        if (lp.asmtLst.GetDimLen(0) != li.nodCnt || lp.asmtLst.GetDimLen(1) != S || lp.biasVec.GetEleCnt() != li.nodCnt) {
+          SetError("layer %d: FC parameter shapes do not match the layer table", l + 1);
+          rc = 1;
+          break;
+        }
+        rc = qcnn_fc_layer_create(ctx, Din, li.nodCnt, S, K, d, lp.ctrdLst.GetDataPtr(), lp.asmtLst.GetDataPtr(),
+                                  lp.biasVec.GetDataPtr(), &nl.pq);
+        if (rc) break;
+        // first FC layer: the reference permutes its NHWC input to NCHW first (CaffeEva.cc:236-238)
+        if (!seenFc && (H > 1 || W > 1)) rc = qcnn_fc_layer_set_src_nhwc(nl.pq, H, W, C);
+        seenFc = true;
+        H = 1; W = 1; C = li.nodCnt;
+        break;
+      }
+      case ENUM_LyrType::Pool:
+        H = PoolOut(H, li.padSiz, li.knlSiz, li.stride);
+        W = PoolOut(W, li.padSiz, li.knlSiz, li.stride);
+        break;
+      default:
+        break;
+    }
+    nl.Hout = H; nl.Wout = W; nl.Cout = C;
+    net->layers.push_back(nl);
+  }
+  if (rc) {
+    qcnn_net_destroy(net);
+    return rc;
+  }
+  // the first conv reads the NCHW API input directly when it runs the strided kernel
+  if (!net->layers.empty() && net->layers[0].pq && net->layers[0].info.type == QCNN_CONV &&
+      net->layers[0].info.stride > 1)
+    qcnn_conv_layer_set_src_nchw(net->layers[0].pq, 1);
+  const size_t L = net->layers.size();
+  net->mapPtr.assign(L + 1, nullptr);
+  net->evBeg.resize(L); net->evEnd.resize(L); net->evUsed.assign(L, 0);
+  for (size_t l = 0; l < L; l++) {
+    cudaEventCreate(&net->evBeg[l]);
+    cudaEventCreate(&net->evEnd[l]);
+  }
+  *out = net;
+  return 0;
+}
+
+extern "C" {
+
+int qcnn_net_create(qcnn_ctx* ctx, const char* model_name, const char* dir, const char* pfx, qcnn_net** out) {
+  QCNN_CHECK(ctx && model_name && dir && pfx && out, "qcnn_net_create: NULL argument");
+  *out = nullptr;
+  CaffePara para;
+  para.Init(dir, pfx);
+  QCNN_CHECK(para.ConfigLayer_ByName(model_name), "qcnn_net_create: unrecognized caffe model name: %s", model_name);
+  QCNN_CHECK(para.LoadLayerPara(true, ENUM_AsmtEnc::Compact), "qcnn_net_create: could not load parameters from %s/%s.*",
+             dir, pfx);
+  return BuildNet(ctx, para, out);
+}
+
+int qcnn_net_create_custom(qcnn_ctx* ctx, int layer_cnt, const qcnn_layer_info* layers, int img_chn, int img_hei,
+                           int img_wid, const char* dir, const char* pfx, qcnn_net** out) {
+  QCNN_CHECK(ctx && layers && dir && pfx && out && layer_cnt >= 1, "qcnn_net_create_custom: bad argument");
+  *out = nullptr;
+  CaffePara para;
+  para.Init(dir, pfx);
+  para.layerCnt = layer_cnt;
+  para.imgChnIn = img_chn; para.imgHeiIn = img_hei; para.imgWidIn = img_wid;
+  para.layerInfoLst.resize(layer_cnt);
+  for (int l = 0; l < layer_cnt; l++) {
+    LayerInfo& li = para.layerInfoLst[l];
+    QCNN_CHECK(layers[l].type >= 0 && layers[l].type <= QCNN_SMAX, "qcnn_net_create_custom: layer %d has invalid type", l);
+    li.type = static_cast<ENUM_LyrType>(layers[l].type);
+    li.padSiz = layers[l].padSiz; li.knlSiz = layers[l].knlSiz; li.knlCnt = layers[l].knlCnt;
+    li.grpCnt = layers[l].grpCnt; li.stride = layers[l].stride; li.nodCnt = layers[l].nodCnt;
+    li.lrnSiz = layers[l].lrnSiz; li.lrnAlp = layers[l].lrnAlp; li.lrnBet = layers[l].lrnBet;
+    li.lrnIni = layers[l].lrnIni; li.drpRat = layers[l].drpRat;
+  }
+  QCNN_CHECK(para.LoadLayerPara(true, ENUM_AsmtEnc::Compact),
+             "qcnn_net_create_custom: could not load parameters from %s/%s.*", dir, pfx);
+  return BuildNet(ctx, para, out);
+}
+
+void qcnn_net_destroy(qcnn_net* net) {
+  if (!net) return;
+  cudaSetDevice(net->ctx->device);
+  FreeMaps(net);
+  for (NetLayer& L : net->layers) qcnn_layer_destroy(L.pq);
+  for (size_t l = 0; l < net->evBeg.size(); l++) {
+    cudaEventDestroy(net->evBeg[l]);
+    cudaEventDestroy(net->evEnd[l]);
+  }
+  for (int i = 0; i < 2; i++) {
+    if (net->d_in[i]) cudaFree(net->d_in[i]);
+    if (net->stCopy) { cudaEventDestroy(net->evH2D[i]); cudaEventDestroy(net->evDone[i]); }
+  }
+  if (net->d_prob) cudaFree(net->d_prob);
+  if (net->d_logit) cudaFree(net->d_logit);
+  if (net->stCopy) cudaStreamDestroy(net->stCopy);
+  if (net->stComp) cudaStreamDestroy(net->stComp);
+  delete net;
+}
+
+int qcnn_net_layer_count(const qcnn_net* net) { return net ? static_cast<int>(net->layers.size()) : 0; }
+
+int qcnn_net_out_len(const qcnn_net* net) {
+  if (!net || net->layers.empty()) return 0;
+  const NetLayer& L = net->layers.back();
+  return L.Hout * L.Wout * L.Cout;
+}
+
+int qcnn_net_set_keep_maps(qcnn_net* net, int keep) {
+  QCNN_CHECK(net, "qcnn_net_set_keep_maps: NULL net");
+  net->keep = keep ? 1 : 0;
+  return 0;
+}
+
+int qcnn_net_set_profiling(qcnn_net* net, int enable) {
+  QCNN_CHECK(net, "qcnn_net_set_profiling: NULL net");
+  net->profiling = enable ? 1 : 0;
+  return 0;
+}
+
+qcnn_layer* qcnn_net_pq_layer(qcnn_net* net, int l) {
+  if (!net || l < 0 || l >= static_cast<int>(net->layers.size())) return nullptr;
+  return net->layers[l].pq;
+}
+
+int qcnn_net_launch_count(const qcnn_net* net) { return net ? static_cast<int>(net->lastLaunches) : 0; }
+
+int qcnn_net_forward(qcnn_net* net, const float* img, int N, float* prob, float* logits, void* stream) {
+  QCNN_CHECK(net && img && prob, "qcnn_net_forward: NULL argument");
+  QCNN_CHECK(N >= 1, "qcnn_net_forward: N must be >= 1");
+  qcnn_ctx* ctx = net->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = EnsureCapacity(net, N)) return rc;
+  const int L = static_cast<int>(net->layers.size());
+  const unsigned long long launches0 = ctx->launches;
+  std::fill(net->mapPtr.begin(), net->mapPtr.end(), nullptr);
+  std::fill(net->evUsed.begin(), net->evUsed.end(), 0);
+
+  // featMapLst[0]: NHWC copy of the input unless the first conv consumes NCHW directly
+  const float* cur = nullptr;
+  const bool firstReadsNchw = L > 0 && net->layers[0].pq && net->layers[0].pq->kind == QCNN_KIND_CONV &&
+                              net->layers[0].pq->src_nchw;
+  if (firstReadsNchw && !net->keep) {
+    cur = img;
+  } else {
+    if (firstReadsNchw) {
+      cur = img;  // conv still reads the NCHW input; also materialise the NHWC map for inspection
+      if (int rc = LaunchNchwToNhwc(ctx, img, net->maps[0], N, net->imgC, net->imgH, net->imgW, st)) return rc;
+    } else {
+      if (int rc = LaunchNchwToNhwc(ctx, img, net->maps[0], N, net->imgC, net->imgH, net->imgW, st)) return rc;
+      cur = net->maps[0];
+    }
+    net->mapPtr[0] = net->maps[0];
+  }
+
+  int l = 0;
+  while (l < L) {
+    NetLayer& nl = net->layers[l];
+    const int type = nl.info.type;
+    const int first = l;
+    if (net->profiling) { QCNN_CUDA(cudaEventRecord(net->evBeg[first], st)); }
+    int rc = 0;
+    const bool lastLayer = (l == L - 1);
+    switch (type) {
+      case QCNN_CONV:
+      case QCNN_FCNT: {
+        const bool fuse = !net->keep && l + 1 < L && net->layers[l + 1].info.type == QCNN_RELU;
+        const int outIdx = fuse ? l + 2 : l + 1;
+        float* dst = net->maps[outIdx];
+        if (type == QCNN_CONV) rc = LaunchConv(nl.pq, cur, N, dst, fuse ? 1 : 0, st);
+        else rc = LaunchFc(nl.pq, cur, N, dst, fuse ? 1 : 0, st);
+        net->mapPtr[outIdx] = dst;
+        cur = dst;
+        l = outIdx;
+        break;
+      }
+      case QCNN_RELU: {
+        float* dst = net->maps[l + 1];
+        rc = LaunchRelu(ctx, cur, dst, static_cast<size_t>(N) * MapElems(nl), st);
+        net->mapPtr[l + 1] = dst; cur = dst; l++;
+        break;
+      }
+      case QCNN_LORN: {
+        const bool fuse = !net->keep && l + 1 < L && net->layers[l + 1].info.type == QCNN_POOL;
+        if (fuse) {
+          const NetLayer& pl = net->layers[l + 1];
+          float* dst = net->maps[l + 2];
+          rc = LaunchLrnMaxPool(ctx, cur, dst, N, nl.Hin, nl.Win, nl.Cin, nl.info.lrnSiz, nl.info.lrnAlp,
+                                nl.info.lrnBet, nl.info.lrnIni, pl.info.knlSiz, pl.info.padSiz, pl.info.stride, st);
+          net->mapPtr[l + 2] = dst; cur = dst; l += 2;
+        } else {
+          float* dst = net->maps[l + 1];
+          rc = LaunchLrn(ctx, cur, dst, static_cast<size_t>(N) * nl.Hin * nl.Win, nl.Cin, nl.info.lrnSiz,
+                         nl.info.lrnAlp, nl.info.lrnBet, nl.info.lrnIni, st);
+          net->mapPtr[l + 1] = dst; cur = dst; l++;
+        }
+        break;
+      }
+      case QCNN_POOL: {
+        float* dst = net->maps[l + 1];
+        rc = LaunchMaxPool(ctx, cur, dst, N, nl.Hin, nl.Win, nl.Cin, nl.info.knlSiz, nl.info.padSiz, nl.info.stride, st);
+        net->mapPtr[l + 1] = dst; cur = dst; l++;
+        break;
+      }
+      case QCNN_DRPT: {
+        if (net->keep) {
+          float* dst = net->maps[l + 1];
+          QCNN_CUDA(cudaMemcpyAsync(dst, cur, sizeof(float) * N * MapElems(nl), cudaMemcpyDeviceToDevice, st));
+          net->mapPtr[l + 1] = dst; cur = dst;
+        } else {
+          net->mapPtr[l + 1] = cur;  // identity: alias
+        }
+        l++;
+        break;
+      }
+      case QCNN_SMAX: {
+        if (logits && lastLayer)
+          QCNN_CUDA(cudaMemcpyAsync(logits, cur, sizeof(float) * N * MapElems(nl), cudaMemcpyDeviceToDevice, st));
+        float* dst = lastLayer ? prob : net->maps[l + 1];
+        rc = LaunchSoftmax(ctx, cur, dst, N, nl.Hout * nl.Wout * nl.Cout, st);
+        net->mapPtr[l + 1] = dst; cur = dst; l++;
+        break;
+      }
+      default:
+        SetError("qcnn_net_forward: invalid layer type %d", type);
+        return 1;
+    }
+    if (rc) return rc;
+    if (net->profiling) {
+      QCNN_CUDA(cudaEventRecord(net->evEnd[first], st));
+      net->evUsed[first] = 1;
+    }
+  }
+  // networks that do not end in softmax: copy the last map out
+  if (L == 0 || net->layers[L - 1].info.type != QCNN_SMAX) {
+    QCNN_CUDA(cudaMemcpyAsync(prob, cur, sizeof(float) * N * qcnn_net_out_len(net), cudaMemcpyDeviceToDevice, st));
+    if (logits) QCNN_CUDA(cudaMemcpyAsync(logits, cur, sizeof(float) * N * qcnn_net_out_len(net), cudaMemcpyDeviceToDevice, st));
+  }
+  net->lastLaunches = ctx->launches - launches0;
+  return 0;
+}
+
+int qcnn_net_forward_h(qcnn_net* net, const float* img_h, int N, float* prob_h, float* logits_h) {
+  QCNN_CHECK(net && img_h && prob_h, "qcnn_net_forward_h: NULL argument");
+  QCNN_CHECK(N >= 1, "qcnn_net_forward_h: N must be >= 1");
+  QCNN_CUDA(cudaSetDevice(net->ctx->device));
+  if (!net->stCopy) {
+    QCNN_CUDA(cudaStreamCreateWithFlags(&net->stCopy, cudaStreamNonBlocking));
+    QCNN_CUDA(cudaStreamCreateWithFlags(&net->stComp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      QCNN_CUDA(cudaEventCreateWithFlags(&net->evH2D[i], cudaEventDisableTiming));
+      QCNN_CUDA(cudaEventCreateWithFlags(&net->evDone[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t imgLen = static_cast<size_t>(net->imgC) * net->imgH * net->imgW;
+  const int outLen = qcnn_net_out_len(net);
+  const int chunk = std::min(N, net->chunk);
+  if (static_cast<size_t>(chunk) > net->d_in_cap) {
+    for (int i = 0; i < 2; i++) {
+      if (net->d_in[i]) QCNN_CUDA(cudaFree(net->d_in[i]));
+      net->d_in[i] = nullptr;
+      QCNN_CUDA(cudaMalloc(&net->d_in[i], sizeof(float) * chunk * imgLen));
+    }
+    net->d_in_cap = chunk;
+  }
+  if (static_cast<size_t>(N) > net->d_out_cap) {
+    if (net->d_prob) QCNN_CUDA(cudaFree(net->d_prob));
+    if (net->d_logit) QCNN_CUDA(cudaFree(net->d_logit));
+    net->d_prob = net->d_logit = nullptr;
+    QCNN_CUDA(cudaMalloc(&net->d_prob, sizeof(float) * N * outLen));
+    QCNN_CUDA(cudaMalloc(&net->d_logit, sizeof(float) * N * outLen));
+    net->d_out_cap = N;
+  }
+  // chunk pipeline: H2D of chunk c+1 (copy stream) overlaps the forward pass of chunk c (compute stream)
+  unsigned long long launches = 0;
+  int ci = 0;
+  for (int n0 = 0; n0 < N; n0 += chunk, ci++) {
+    const int cn = std::min(chunk, N - n0);
+    const int b = ci & 1;
+    if (ci >= 2) QCNN_CUDA(cudaStreamWaitEvent(net->stCopy, net->evDone[b], 0));
+    QCNN_CUDA(cudaMemcpyAsync(net->d_in[b], img_h + n0 * imgLen, sizeof(float) * cn * imgLen, cudaMemcpyHostToDevice,
+                              net->stCopy));
+    QCNN_CUDA(cudaEventRecord(net->evH2D[b], net->stCopy));
+    QCNN_CUDA(cudaStreamWaitEvent(net->stComp, net->evH2D[b], 0));
+    if (int rc = qcnn_net_forward(net, net->d_in[b], cn, net->d_prob + static_cast<size_t>(n0) * outLen,
+                                  logits_h ? net->d_logit + static_cast<size_t>(n0) * outLen : nullptr, net->stComp))
+      return rc;
+    launches += net->lastLaunches;
+    QCNN_CUDA(cudaEventRecord(net->evDone[b], net->stComp));
+  }
+  QCNN_CUDA(cudaMemcpyAsync(prob_h, net->d_prob, sizeof(float) * N * outLen, cudaMemcpyDeviceToHost, net->stComp));
+  if (logits_h)
+    QCNN_CUDA(cudaMemcpyAsync(logits_h, net->d_logit, sizeof(float) * N * outLen, cudaMemcpyDeviceToHost, net->stComp));
+  QCNN_CUDA(cudaStreamSynchronize(net->stComp));
+  net->lastLaunches = launches;
+  return 0;
+}
+
+int qcnn_net_set_chunk(qcnn_net* net, int chunk) {
+  QCNN_CHECK(net && chunk >= 1, "qcnn_net_set_chunk: bad argument");
+  net->chunk = chunk;
+  return 0;
+}
+
+int qcnn_net_featmap(qcnn_net* net, int idx, const float** ptr, int* dims4) {
+  QCNN_CHECK(net && ptr && dims4, "qcnn_net_featmap: NULL argument");
+  const int L = static_cast<int>(net->layers.size());
+  QCNN_CHECK(idx >= 0 && idx <= L, "qcnn_net_featmap: index %d out of range", idx);
+  *ptr = net->mapPtr[idx];
+  if (idx == 0) { dims4[1] = net->imgH; dims4[2] = net->imgW; dims4[3] = net->imgC; }
+  else { const NetLayer& nl = net->layers[idx - 1]; dims4[1] = nl.Hout; dims4[2] = nl.Wout; dims4[3] = nl.Cout; }
+  dims4[0] = 0;
+  return 0;
+}
+
+int qcnn_net_layer_time_ms(qcnn_net* net, int layer, float* ms) {
+  QCNN_CHECK(net && ms, "qcnn_net_layer_time_ms: NULL argument");
+  QCNN_CHECK(layer >= 0 && layer < static_cast<int>(net->layers.size()), "qcnn_net_layer_time_ms: bad layer index");
+  *ms = 0.0f;
+  if (!net->evUsed[layer]) return 0;
+  QCNN_CUDA(cudaEventSynchronize(net->evEnd[layer]));
+  QCNN_CUDA(cudaEventElapsedTime(ms, net->evBeg[layer], net->evEnd[layer]));
+  return 0;
+}
+
+int qcnn_net_layer_work(qcnn_net* net, int layer, int N, double* alg_bytes, double* lookups, double* lut_macs) {
+  QCNN_CHECK(net, "qcnn_net_layer_work: NULL net");
+  QCNN_CHECK(layer >= 0 && layer < static_cast<int>(net->layers.size()), "qcnn_net_layer_work: bad layer index");
+  const NetLayer& nl = net->layers[layer];
+  if (nl.pq) return qcnn_layer_work(nl.pq, N, alg_bytes, lookups, lut_macs);
+  // non-PQ layers stream their input and output maps once
+  const double in = 4.0 * N * nl.Hin * nl.Win * nl.Cin, outb = 4.0 * N * nl.Hout * nl.Wout * nl.Cout;
+  if (alg_bytes) *alg_bytes = (nl.info.type == QCNN_DRPT) ? 0.0 : in + outb;
+  if (lookups) *lookups = 0.0;
+  if (lut_macs) *lut_macs = 0.0;
+  return 0;
+}
+
+}  // extern "C"

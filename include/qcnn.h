@@ -45,6 +45,14 @@ QCNN_API void qcnn_ctx_destroy(qcnn_ctx* ctx);
 QCNN_API int qcnn_ctx_device(const qcnn_ctx* ctx);
 QCNN_API int qcnn_ctx_sm_count(const qcnn_ctx* ctx);
 
+/* device-memory helpers: a host program (e.g. the reference's CaffeEva.cc) can drive the library without the CUDA
+ * toolkit.  Copies are asynchronous on `stream` when the host buffer is pinned; qcnn_stream_sync waits for it. */
+QCNN_API int qcnn_dev_alloc(qcnn_ctx* ctx, size_t bytes, void** out);
+QCNN_API int qcnn_dev_free(qcnn_ctx* ctx, void* ptr);
+QCNN_API int qcnn_copy_h2d(qcnn_ctx* ctx, void* dst, const void* src_h, size_t bytes, void* stream);
+QCNN_API int qcnn_copy_d2h(qcnn_ctx* ctx, void* dst_h, const void* src, size_t bytes, void* stream);
+QCNN_API int qcnn_stream_sync(qcnn_ctx* ctx, void* stream);
+
 /* ---- PQ layers (one-time set-up) ---------------------------------------------------------------------------
  * Take the HOST arrays exactly as CaffePara::layerParaLst[l] holds them and do the re-layout + upload that
  * CaffeEva::PrepCtrdBuf / PrepAsmtBuf (src/CaffeEva.cc:534-623) do on the CPU.
@@ -67,6 +75,8 @@ QCNN_API int qcnn_conv_layer_set_src_nchw(qcnn_layer* layer, int enable);
 /* tuning overrides for tests/benchmarks: "fc_nsplit" (subspace splits, 0 = automatic; 1 reproduces the reference's
  * accumulation order exactly), "fc_tn" (images per CTA: 1, 4 or 8; 0 = automatic) */
 QCNN_API int qcnn_layer_set_param(qcnn_layer* layer, const char* name, int value);
+/* one-line description of the kernel + tiling chosen for batch N */
+QCNN_API int qcnn_layer_describe(qcnn_layer* layer, int N, char* buf, size_t cap);
 QCNN_API void qcnn_layer_destroy(qcnn_layer* layer);
 /* out[0..2] = Ho, Wo, Cout (FC: 1, 1, Dout) */
 QCNN_API int qcnn_layer_out_dims(const qcnn_layer* layer, int* out3);

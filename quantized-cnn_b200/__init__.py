@@ -58,11 +58,17 @@ _SIGS = {
     "qcnn_ctx_destroy": (None, [_vp]),
     "qcnn_ctx_device": (_i, [_vp]),
     "qcnn_ctx_sm_count": (_i, [_vp]),
+    "qcnn_dev_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "qcnn_dev_free": (_i, [_vp, _vp]),
+    "qcnn_copy_h2d": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "qcnn_copy_d2h": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "qcnn_stream_sync": (_i, [_vp, _vp]),
     "qcnn_conv_layer_create": (_i, [_vp] + [_i] * 11 + [_vp, _vp, _vp, C.POINTER(_vp)]),
     "qcnn_fc_layer_create": (_i, [_vp] + [_i] * 5 + [_vp, _vp, _vp, C.POINTER(_vp)]),
     "qcnn_fc_layer_set_src_nhwc": (_i, [_vp, _i, _i, _i]),
     "qcnn_conv_layer_set_src_nchw": (_i, [_vp, _i]),
     "qcnn_layer_set_param": (_i, [_vp, _cp, _i]),
+    "qcnn_layer_describe": (_i, [_vp, _i, _cp, _sz]),
     "qcnn_layer_destroy": (None, [_vp]),
     "qcnn_layer_out_dims": (_i, [_vp, C.POINTER(_i)]),
     "qcnn_layer_work": (_i, [_vp, _i, _dp, _dp, _dp]),
@@ -221,6 +227,11 @@ class _Layer(object):
         b, l, m = C.c_double(), C.c_double(), C.c_double()
         _check(lib.qcnn_layer_work(self.h, N, C.byref(b), C.byref(l), C.byref(m)))
         return dict(alg_bytes=b.value, lookups=l.value, lut_macs=m.value)
+
+    def describe(self, N):
+        buf = C.create_string_buffer(512)
+        _check(lib.qcnn_layer_describe(self.h, N, buf, 512))
+        return buf.value.decode()
 
     def set_param(self, name, value):
         _check(lib.qcnn_layer_set_param(self.h, name.encode(), value))

@@ -89,6 +89,35 @@ __global__ void lrn_maxpool_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
+// Tiled variant: one CTA per (image, output row).  The <= ksz input rows the row needs are normalised ONCE into
+// shared memory and then pooled, so the expf/logf pair runs ~ksz/stride times per input element instead of
+// ksz^2/stride^2 times, and the normalised map still never reaches HBM.
+__global__ void lrn_maxpool_tiled_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int C,
+                                         int Ho, int Wo, int size, float coeff, float kini, float nbeta, int ksz,
+                                         int pad, int stride) {
+  extern __shared__ float tile[];  // [rows][W][C]
+  const int rad = (size - 1) / 2;
+  const int ho = blockIdx.x, n = blockIdx.y;
+  const int hL = max(0, ho * stride - pad), hU = min(H, ho * stride + ksz - pad) - 1;
+  const int rows = hU - hL + 1;
+  const int rowLen = W * C;
+  const float* base = src + (static_cast<size_t>(n) * H + hL) * rowLen;
+  for (int e = threadIdx.x; e < rows * rowLen; e += blockDim.x) {
+    const int p = e / C, c = e - p * C;
+    tile[e] = LrnAt(base + static_cast<size_t>(p) * C, c, C, size, rad, coeff, kini, nbeta);
+  }
+  __syncthreads();
+  float* out = dst + (static_cast<size_t>(n) * Ho + ho) * Wo * C;
+  for (int e = threadIdx.x; e < Wo * C; e += blockDim.x) {
+    const int wo = e / C, c = e - wo * C;
+    const int wL = max(0, wo * stride - pad), wU = min(W, wo * stride + ksz - pad) - 1;
+    float m = -INFINITY;
+    for (int r = 0; r < rows; r++)
+      for (int w = wL; w <= wU; w++) m = fmaxf(m, tile[(r * W + w) * C + c]);
+    out[e] = m;
+  }
+}
+
 // CalcFeatMap_SMax (CaffeEva.cc:1098-1116): y = exp(x) / sum(exp(x)), NO max subtraction (kept: parity).
 // One CTA per image; the float sum is reduced in a fixed tree order (deterministic).
 __global__ void softmax_kernel(const float* __restrict__ src, float* __restrict__ dst, int C) {
@@ -188,8 +217,17 @@ int LaunchLrnMaxPool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, 
   QCNN_CHECK(N >= 1 && ksz >= 1 && stride >= 1 && size >= 1, "qcnn_lrn_maxpool: bad arguments");
   const int Ho = PoolOut(H, pad, ksz, stride), Wo = PoolOut(W, pad, ksz, stride);
   const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
-  lrn_maxpool_kernel<<<GridFor(ctx, total), kThreads, 0, st>>>(src, dst, N, H, W, C, Ho, Wo, size, alpha / size, k,
-                                                               -beta, ksz, pad, stride);
+  const size_t tileBytes = sizeof(float) * static_cast<size_t>(ksz) * W * C;
+  if (tileBytes <= 160 * 1024 && N <= 65535) {
+    auto kern = lrn_maxpool_tiled_kernel;
+    if (tileBytes > 48 * 1024)
+      QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileBytes));
+    kern<<<dim3(Ho, N), kThreads, tileBytes, st>>>(src, dst, H, W, C, Ho, Wo, size, alpha / size, k, -beta, ksz, pad,
+                                                   stride);
+  } else {
+    lrn_maxpool_kernel<<<GridFor(ctx, total), kThreads, 0, st>>>(src, dst, N, H, W, C, Ho, Wo, size, alpha / size, k,
+                                                                 -beta, ksz, pad, stride);
+  }
   QCNN_CUDA(cudaGetLastError());
   ctx->launches++;
   return 0;

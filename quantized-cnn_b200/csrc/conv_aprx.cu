@@ -10,10 +10,15 @@
 //     is warp-uniform, so the 32 lanes read 32 consecutive floats (one wavefront, no conflicts);
 //   * zero padding is realised by zero LUT columns (padded flat grid), so no per-lane bounds predicate exists in
 //     the inner loop -- out-of-image taps add +0.0f, which is what the reference's tap skipping amounts to;
-//   * a thread owns J positions x CPT channels (<= 64 accumulators); per 4 channels it issues one 128-bit
-//     broadcast load of 4 pre-multiplied LUT row offsets, then 4 x (1 IADD + J LDS + J FADD);
+//   * a thread owns J positions x CPT channels (<= 64 accumulators, held as float2 pairs so two positions are
+//     accumulated by one FADD2); per 4 channels it issues one 128-bit broadcast load of 4 pre-multiplied LUT row
+//     offsets, then 4 x (1 IADD + J LDS + J/2 FADD2);
 //   * the per-(s) assignment slice is staged in shared memory already multiplied by the LUT row pitch.
-// Two kernels share that inner loop:
+// The LUT stage is a [K x d] x [d x positions] contraction per subspace.  It runs on the FP32 pipe as a
+// register-blocked mini-GEMM: 8 codewords x 4 positions per thread, packed FFMA2 (two FMAs per issue slot), codebook
+// rows broadcast from shared memory, 128-bit LUT stores.  (fp32, ascending j: parity with the reference's saxpy
+// order up to FMA contraction; tensor-core TF32 would break the fp32 tolerance -- SURVEY.md 7.5.)
+// Two kernels share both stages:
 //   conv_s1_kernel   stride 1 (conv2..conv5, sweep): a CTA owns (image, row strip, group, channel tile) and the
 //                    flat padded grid of the strip; tap (kh,kw) is a constant shift kh*PW+kw of the position.
 //   conv_roll_kernel any stride (conv1: 11x11 / 4): a CTA walks the input rows of its strip once; each input
@@ -30,65 +35,126 @@ namespace {
 constexpr int kMaxThreads = 512;
 
 // ------------------------------------------------------------------------------------------------------------
-// LUT slice build shared by both kernels: lut[k][pos] (+)= sum_{jj<8} x[jj] * cb[k][jj]  for k in [kbeg,kend)
+// staging helpers
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void BuildColumn(float* __restrict__ lut, const float* __restrict__ cb, int PP, int pos,
-                                            int kbeg, int kend, const float (&x)[8], bool first, bool narrow) {
-  if (narrow) {  // only x[0..3] are non-zero (d <= 4 or last partial chunk): half the FMAs
-#pragma unroll 4
-    for (int k = kbeg; k < kend; k++) {
-      const float4 c0 = *reinterpret_cast<const float4*>(cb + k * 8);
-      float v = first ? 0.0f : lut[k * PP + pos];
-      v = fmaf(x[0], c0.x, v);
-      v = fmaf(x[1], c0.y, v);
-      v = fmaf(x[2], c0.z, v);
-      v = fmaf(x[3], c0.w, v);
-      lut[k * PP + pos] = v;
-    }
-  } else {
-#pragma unroll 4
-    for (int k = kbeg; k < kend; k++) {
-      const float4 c0 = *reinterpret_cast<const float4*>(cb + k * 8);
-      const float4 c1 = *reinterpret_cast<const float4*>(cb + k * 8 + 4);
-      float v = first ? 0.0f : lut[k * PP + pos];
-      v = fmaf(x[0], c0.x, v);
-      v = fmaf(x[1], c0.y, v);
-      v = fmaf(x[2], c0.z, v);
-      v = fmaf(x[3], c0.w, v);
-      v = fmaf(x[4], c1.x, v);
-      v = fmaf(x[5], c1.y, v);
-      v = fmaf(x[6], c1.z, v);
-      v = fmaf(x[7], c1.w, v);
-      lut[k * PP + pos] = v;
-    }
+// cb2[jj][k] = (c, c) with c = ctrd[s][k][jc + jj]  (zero beyond the subspace's real dims)
+__device__ __forceinline__ void StageCodebook(float2* __restrict__ cb2, const float* __restrict__ ctrd, int s, int K,
+                                              int d, int jc, int nj, int tid, int T) {
+  for (int e = tid; e < K * 8; e += T) {
+    const int k = e >> 3, jj = e & 7;
+    const float c = (jj < nj) ? __ldg(ctrd + (static_cast<size_t>(s) * K + k) * d + jc + jj) : 0.0f;
+    cb2[jj * K + k] = make_float2(c, c);
   }
 }
 
-// gather of one tap: acc[j][c] += lut[idx[c]][q_j + shift]; `base` = byte address of lut[0][q_0 + shift]
+// idx[tap][c] = asmt[tap][c] * (PP * 4)  -> byte offset of LUT row k
+__device__ __forceinline__ void StageOffsets(uint32_t* __restrict__ idx, const uint8_t* __restrict__ ap, int taps,
+                                             int CT, int KgPad, uint32_t rowBytes, int tid, int T) {
+  for (int e = tid; e < taps * CT; e += T) {
+    const int tap = e / CT, c = e - tap * CT;
+    idx[e] = static_cast<uint32_t>(__ldg(ap + tap * KgPad + c)) * rowBytes;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LUT stage: lut[k][p] (+)= sum_{jj<nj} cb[jj][k] * xs[jj][p], tile of 8 codewords x 4 positions per thread.
+// Lanes walk the position tiles (128-bit LUT stores and x loads are conflict-free, codebook loads broadcast).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void BuildLut(float* __restrict__ lut, const float2* __restrict__ cb2,
+                                         const float* __restrict__ xs, int K, int PP, int nj, bool first, int tid,
+                                         int T) {
+  const int npt = PP >> 2;
+  const int ntiles = npt * (K >> 3);
+  for (int t = tid; t < ntiles; t += T) {
+    const int kt = t / npt;
+    const int p0 = (t - kt * npt) << 2;
+    const int k0 = kt << 3;
+    float2 acc[8][2];
+    if (first) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) { acc[k][0] = make_float2(0.f, 0.f); acc[k][1] = make_float2(0.f, 0.f); }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float4 v = *reinterpret_cast<const float4*>(lut + (k0 + k) * PP + p0);
+        acc[k][0] = make_float2(v.x, v.y);
+        acc[k][1] = make_float2(v.z, v.w);
+      }
+    }
+#pragma unroll 2
+    for (int j = 0; j < nj; j++) {
+      const float4 xv = *reinterpret_cast<const float4*>(xs + j * PP + p0);
+      const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
+      const float4* cp = reinterpret_cast<const float4*>(cb2 + j * K + k0);
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const float4 cc = cp[kk];  // (c[2kk], c[2kk], c[2kk+1], c[2kk+1])
+        const float2 ca = make_float2(cc.x, cc.y), cb = make_float2(cc.z, cc.w);
+        acc[2 * kk][0] = __ffma2_rn(ca, x01, acc[2 * kk][0]);
+        acc[2 * kk][1] = __ffma2_rn(ca, x23, acc[2 * kk][1]);
+        acc[2 * kk + 1][0] = __ffma2_rn(cb, x01, acc[2 * kk + 1][0]);
+        acc[2 * kk + 1][1] = __ffma2_rn(cb, x23, acc[2 * kk + 1][1]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      *reinterpret_cast<float4*>(lut + (k0 + k) * PP + p0) = make_float4(acc[k][0].x, acc[k][0].y, acc[k][1].x, acc[k][1].y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// gather stage
+// ------------------------------------------------------------------------------------------------------------
+// Accumulators of one thread: J positions x CPT channels.  For even J two positions share a float2 so that one
+// FADD2 retires two lookups.
 template <int CPT, int J>
-__device__ __forceinline__ void GatherTap(float (&acc)[J][CPT], const char* base, const uint32_t* __restrict__ ip) {
+struct Acc {
+  static constexpr int JP = (J % 2 == 0) ? J / 2 : J;
+  static constexpr bool kPaired = (J % 2 == 0);
+  float2 v[JP][CPT];  // paired: (pos 2jp, pos 2jp+1); unpaired: .x only
+
+  __device__ __forceinline__ void Fill(const float (&b)[CPT]) {
+#pragma unroll
+    for (int jp = 0; jp < JP; jp++)
+#pragma unroll
+      for (int c = 0; c < CPT; c++) v[jp][c] = make_float2(b[c], b[c]);
+  }
+  __device__ __forceinline__ float Get(int j, int c) const {
+    if (kPaired) return (j & 1) ? v[j >> 1][c].y : v[j >> 1][c].x;
+    return v[j][c].x;
+  }
+};
+
+// one tap: acc[j][c] += lut[idx[c]][q_j + shift]; `base` = byte address of lut[0][q_0 + shift]; positions of a
+// thread are 32 apart (j * 128 bytes), so the J loads of a channel share one address register.
+template <int CPT, int J>
+__device__ __forceinline__ void GatherTap(Acc<CPT, J>& acc, const char* base, const uint32_t* __restrict__ ip) {
 #pragma unroll
   for (int c4 = 0; c4 < CPT; c4 += 4) {
     const uint4 o = *reinterpret_cast<const uint4*>(ip + c4);
-    const char* b0 = base + o.x;
-    const char* b1 = base + o.y;
-    const char* b2 = base + o.z;
-    const char* b3 = base + o.w;
+    const char* b[4] = {base + o.x, base + o.y, base + o.z, base + o.w};
 #pragma unroll
-    for (int j = 0; j < J; j++) {
-      acc[j][c4 + 0] += *reinterpret_cast<const float*>(b0 + j * 128);
-      acc[j][c4 + 1] += *reinterpret_cast<const float*>(b1 + j * 128);
-      acc[j][c4 + 2] += *reinterpret_cast<const float*>(b2 + j * 128);
-      acc[j][c4 + 3] += *reinterpret_cast<const float*>(b3 + j * 128);
+    for (int u = 0; u < 4; u++) {
+      if (Acc<CPT, J>::kPaired) {
+#pragma unroll
+        for (int jp = 0; jp < J / 2; jp++) {
+          const float2 val = make_float2(*reinterpret_cast<const float*>(b[u] + (2 * jp) * 128),
+                                         *reinterpret_cast<const float*>(b[u] + (2 * jp + 1) * 128));
+          acc.v[jp][c4 + u] = __fadd2_rn(acc.v[jp][c4 + u], val);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < J; j++) acc.v[j][c4 + u].x += *reinterpret_cast<const float*>(b[u] + j * 128);
+      }
     }
   }
 }
 
-template <int CPT>
-__device__ __forceinline__ void StoreChannels(float* __restrict__ out, const float (&v)[CPT], int relu) {
+template <int CPT, int J>
+__device__ __forceinline__ void StoreChannels(float* __restrict__ out, const Acc<CPT, J>& acc, int j, int relu) {
 #pragma unroll
   for (int c = 0; c < CPT; c += 4) {
-    float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    float4 o = make_float4(acc.Get(j, c), acc.Get(j, c + 1), acc.Get(j, c + 2), acc.Get(j, c + 3));
     if (relu) {
       o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
     }
@@ -96,16 +162,31 @@ __device__ __forceinline__ void StoreChannels(float* __restrict__ out, const flo
   }
 }
 
+struct SmemLayout {
+  float* lut;      // [K][PP]
+  uint32_t* idx;   // [taps][CT]
+  float2* cb2;     // [8][K]
+  float* xs;       // [8][PP]
+};
+
+__device__ __forceinline__ SmemLayout Carve(unsigned char* smem, int K, int PP, int taps, int CT) {
+  SmemLayout s;
+  s.lut = reinterpret_cast<float*>(smem);
+  s.idx = reinterpret_cast<uint32_t*>(s.lut + static_cast<size_t>(K) * PP);
+  s.cb2 = reinterpret_cast<float2*>(s.idx + taps * CT);
+  s.xs = reinterpret_cast<float*>(s.cb2 + 8 * K);
+  return s;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // stride-1 kernel
 // ------------------------------------------------------------------------------------------------------------
-template <int CPT, int J>
-__global__ void __launch_bounds__(kMaxThreads, 1) conv_s1_kernel(const ConvArgs a) {
+// MAXT: launch bound (256 / 384 / 512 threads) -> register cap 255 / 168 / 128, so small CTAs never spill
+template <int CPT, int J, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) conv_s1_kernel(const ConvArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int taps = a.ksz * a.ksz;
-  float* lut = reinterpret_cast<float*>(smem);                      // [K][PP]
-  uint32_t* idx = reinterpret_cast<uint32_t*>(lut + a.K * a.PP);    // [taps][CT] byte offsets k*PP*4
-  float* cb = reinterpret_cast<float*>(idx + taps * a.CT);          // [K][8]
+  const SmemLayout sm = Carve(smem, a.K, a.PP, taps, a.CT);
 
   const int tid = threadIdx.x, T = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -120,58 +201,46 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_s1_kernel(const ConvArgs 
   const int q0 = pw * 32 * J + lane;     // first flat position of this thread (others at +32 j)
   const int cbase = ct * a.CT + cw * CPT;  // first channel (within the group) of this thread
 
-  float acc[J][CPT];
+  Acc<CPT, J> acc;
+  {
+    float bv[CPT];
 #pragma unroll
-  for (int c = 0; c < CPT; c++) {
-    const float bv = __ldg(a.bias + g * a.Kg + cbase + c);
-#pragma unroll
-    for (int j = 0; j < J; j++) acc[j][c] = bv;
+    for (int c = 0; c < CPT; c++) bv[c] = __ldg(a.bias + g * a.Kg + cbase + c);
+    acc.Fill(bv);
   }
 
-  const int kper = a.K / a.ksplit;
   const uint32_t rowBytes = static_cast<uint32_t>(a.PP) * 4u;
   for (int s = 0; s < a.S; s++) {
     const int dsel = min(a.Cg - s * a.d, a.d);  // dims of this subspace that exist (reference CaffeEva.cc:1277)
     // ---- LUT stage ----
     for (int jc = 0; jc == 0 || jc < dsel; jc += 8) {
-      __syncthreads();
-      for (int e = tid; e < a.K * 8; e += T) {
-        const int k = e >> 3, j = jc + (e & 7);
-        cb[e] = (j < dsel) ? __ldg(a.ctrd + (static_cast<size_t>(s) * a.K + k) * a.d + j) : 0.0f;
-      }
-      if (jc == 0) {
-        const uint8_t* ap = a.asmt + (static_cast<size_t>(g) * a.S + s) * taps * a.KgPad + ct * a.CT;
-        for (int e = tid; e < taps * a.CT; e += T) {
-          const int tap = e / a.CT, c = e - tap * a.CT;
-          idx[e] = static_cast<uint32_t>(__ldg(ap + tap * a.KgPad + c)) * rowBytes;
-        }
-      }
-      __syncthreads();
-      const bool narrow = (dsel - jc) <= 4;
-      for (int e = tid; e < a.PP * a.ksplit; e += T) {
-        const int kq = e / a.PP;
-        const int pos = e - kq * a.PP;
-        float x[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) x[jj] = 0.0f;
+      const int nj = max(0, min(8, dsel - jc));
+      __syncthreads();  // previous gather / previous chunk is done with lut, idx, cb2, xs
+      StageCodebook(sm.cb2, a.ctrd, s, a.K, a.d, jc, nj, tid, T);
+      if (jc == 0)
+        StageOffsets(sm.idx, a.asmt + (static_cast<size_t>(g) * a.S + s) * taps * a.KgPad + ct * a.CT, taps, a.CT,
+                     a.KgPad, rowBytes, tid, T);
+      // xs[jj][pos]: input channel (g*Cg + s*d + jc + jj) at LUT position pos, 0 for padding
+      for (int e = tid; e < a.PP * 8; e += T) {
+        const int jj = e / a.PP;
+        const int pos = e - jj * a.PP;
+        float x = 0.0f;
         const int pp = pos - a.pad;
-        if (pp >= 0) {
+        if (jj < nj && pp >= 0) {
           const int ri = pp / a.PW, wi = pp - ri * a.PW;
           const int hi = hin0 + ri;
-          if (ri < a.RI && wi < a.Wi && hi >= 0 && hi < a.Hi) {
-            const float* xp = a.src + ((static_cast<size_t>(n) * a.Hi + hi) * a.Wi + wi) * a.Cin + g * a.Cg + s * a.d + jc;
-#pragma unroll
-            for (int jj = 0; jj < 8; jj++)
-              if (jc + jj < dsel) x[jj] = __ldg(xp + jj);
-          }
+          if (ri < a.RI && wi < a.Wi && hi >= 0 && hi < a.Hi)
+            x = __ldg(a.src + ((static_cast<size_t>(n) * a.Hi + hi) * a.Wi + wi) * a.Cin + g * a.Cg + s * a.d + jc + jj);
         }
-        BuildColumn(lut, cb, a.PP, pos, kq * kper, (kq + 1) * kper, x, jc == 0, narrow);
+        sm.xs[e] = x;
       }
+      __syncthreads();
+      BuildLut(sm.lut, sm.cb2, sm.xs, a.K, a.PP, nj, jc == 0, tid, T);
     }
     __syncthreads();
     // ---- gather stage ----
-    const char* lutq = reinterpret_cast<const char*>(lut) + q0 * 4;
-    const uint32_t* ip = idx + cw * CPT;
+    const char* lutq = reinterpret_cast<const char*>(sm.lut) + q0 * 4;
+    const uint32_t* ip = sm.idx + cw * CPT;
     for (int kh = 0; kh < a.ksz; kh++) {
       for (int kw = 0; kw < a.ksz; kw++) {
         GatherTap<CPT, J>(acc, lutq + (kh * a.PW + kw) * 4, ip);
@@ -187,7 +256,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_s1_kernel(const ConvArgs 
     const int ho = r0 + r;
     if (r < a.R && wo < a.Wo && ho < a.Ho) {
       float* out = a.dst + ((static_cast<size_t>(n) * a.Ho + ho) * a.Wo + wo) * a.Cout + g * a.Kg + cbase;
-      StoreChannels<CPT>(out, acc[j], a.relu);
+      StoreChannels<CPT, J>(out, acc, j, a.relu);
     }
   }
 }
@@ -195,13 +264,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_s1_kernel(const ConvArgs 
 // ------------------------------------------------------------------------------------------------------------
 // rolling-row kernel (any stride)
 // ------------------------------------------------------------------------------------------------------------
-template <int CPT, int J>
-__global__ void __launch_bounds__(kMaxThreads, 1) conv_roll_kernel(const ConvArgs a) {
+template <int CPT, int J, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) conv_roll_kernel(const ConvArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int taps = a.ksz * a.ksz;
-  float* lut = reinterpret_cast<float*>(smem);                      // [K][PP], PP = stride * PH
-  uint32_t* idx = reinterpret_cast<uint32_t*>(lut + a.K * a.PP);    // [taps][CT]
-  float* cb = reinterpret_cast<float*>(idx + taps * a.CT);          // [K][8]
+  const SmemLayout sm = Carve(smem, a.K, a.PP, taps, a.CT);  // PP = stride * PH (rounded)
 
   const int tid = threadIdx.x, T = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -220,16 +287,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_roll_kernel(const ConvArg
   const int cbase = ct * a.CT + cw * CPT;
 
   float bias[CPT];
-  float acc[J][CPT];
 #pragma unroll
-  for (int c = 0; c < CPT; c++) {
-    bias[c] = __ldg(a.bias + g * a.Kg + cbase + c);
-#pragma unroll
-    for (int j = 0; j < J; j++) acc[j][c] = bias[c];
-  }
+  for (int c = 0; c < CPT; c++) bias[c] = __ldg(a.bias + g * a.Kg + cbase + c);
+  Acc<CPT, J> acc;
+  acc.Fill(bias);
   int ho_cur = ho0 + rg;  // output row this warp is accumulating
 
-  const int kper = a.K / a.ksplit;
   const uint32_t rowBytes = static_cast<uint32_t>(a.PP) * 4u;
   const int hi_begin = ho0 * a.stride - a.pad;
   const int hi_end = (ho_end - 1) * a.stride - a.pad + a.ksz;
@@ -242,51 +305,34 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_roll_kernel(const ConvArg
       for (int s = 0; s < a.S; s++) {
         const int dsel = min(a.Cg - s * a.d, a.d);
         for (int jc = 0; jc == 0 || jc < dsel; jc += 8) {
+          const int nj = max(0, min(8, dsel - jc));
           __syncthreads();
-          for (int e = tid; e < a.K * 8; e += T) {
-            const int k = e >> 3, j = jc + (e & 7);
-            cb[e] = (j < dsel) ? __ldg(a.ctrd + (static_cast<size_t>(s) * a.K + k) * a.d + j) : 0.0f;
-          }
+          StageCodebook(sm.cb2, a.ctrd, s, a.K, a.d, jc, nj, tid, T);
           if (jc == 0 && (a.S > 1 || !idx_ready)) {
-            const uint8_t* ap = a.asmt + (static_cast<size_t>(g) * a.S + s) * taps * a.KgPad + ct * a.CT;
-            for (int e = tid; e < taps * a.CT; e += T) {
-              const int tap = e / a.CT, c = e - tap * a.CT;
-              idx[e] = static_cast<uint32_t>(__ldg(ap + tap * a.KgPad + c)) * rowBytes;
-            }
+            StageOffsets(sm.idx, a.asmt + (static_cast<size_t>(g) * a.S + s) * taps * a.KgPad + ct * a.CT, taps, a.CT,
+                         a.KgPad, rowBytes, tid, T);
             idx_ready = true;
           }
-          __syncthreads();
-          const bool narrow = (dsel - jc) <= 4;
-          for (int e = tid; e < a.PP * a.ksplit; e += T) {
-            const int kq = e / a.PP;
-            const int pos = e - kq * a.PP;
+          for (int e = tid; e < a.PP * 8; e += T) {
+            const int jj = e / a.PP;
+            const int pos = e - jj * a.PP;
             const int phase = pos / PH, i = pos - phase * PH;
             const int wi = i * a.stride + phase - a.pad;
-            float x[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; jj++) x[jj] = 0.0f;
-            if (wi >= 0 && wi < a.Wi) {
-              const int ch0 = g * a.Cg + s * a.d + jc;
-              if (a.src_nchw) {
-                const float* xp = a.src + ((static_cast<size_t>(n) * a.Cin + ch0) * a.Hi + hi) * a.Wi + wi;
-                const size_t plane = static_cast<size_t>(a.Hi) * a.Wi;
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++)
-                  if (jc + jj < dsel) x[jj] = __ldg(xp + jj * plane);
-              } else {
-                const float* xp = a.src + ((static_cast<size_t>(n) * a.Hi + hi) * a.Wi + wi) * a.Cin + ch0;
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++)
-                  if (jc + jj < dsel) x[jj] = __ldg(xp + jj);
-              }
+            float x = 0.0f;
+            if (jj < nj && phase < a.stride && wi >= 0 && wi < a.Wi) {
+              const int ch = g * a.Cg + s * a.d + jc + jj;
+              x = a.src_nchw ? __ldg(a.src + ((static_cast<size_t>(n) * a.Cin + ch) * a.Hi + hi) * a.Wi + wi)
+                             : __ldg(a.src + ((static_cast<size_t>(n) * a.Hi + hi) * a.Wi + wi) * a.Cin + ch);
             }
-            BuildColumn(lut, cb, a.PP, pos, kq * kper, (kq + 1) * kper, x, jc == 0, narrow);
+            sm.xs[e] = x;
           }
+          __syncthreads();
+          BuildLut(sm.lut, sm.cb2, sm.xs, a.K, a.PP, nj, jc == 0, tid, T);
         }
         __syncthreads();
         if (active) {
-          const char* lutq = reinterpret_cast<const char*>(lut) + wo0 * 4;
-          const uint32_t* ip = idx + (kh * a.ksz) * a.CT + cw * CPT;
+          const char* lutq = reinterpret_cast<const char*>(sm.lut) + wo0 * 4;
+          const uint32_t* ip = sm.idx + (kh * a.ksz) * a.CT + cw * CPT;
           for (int kw = 0; kw < a.ksz; kw++) {
             const int phase = kw % a.stride, sh = kw / a.stride;
             GatherTap<CPT, J>(acc, lutq + (phase * PH + sh) * 4, ip);
@@ -302,25 +348,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_roll_kernel(const ConvArg
         const int wo = wo0 + 32 * j;
         if (wo < a.Wo) {
           float* out = a.dst + ((static_cast<size_t>(n) * a.Ho + ho_cur) * a.Wo + wo) * a.Cout + g * a.Kg + cbase;
-          StoreChannels<CPT>(out, acc[j], a.relu);
+          StoreChannels<CPT, J>(out, acc, j, a.relu);
         }
-#pragma unroll
-        for (int c = 0; c < CPT; c++) acc[j][c] = bias[c];
       }
+      acc.Fill(bias);
       ho_cur += a.rgroups;
     }
   }
 }
 
-template <int CPT, int J>
-int LaunchOne(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
+template <int CPT, int J, int MAXT>
+int LaunchBound(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
   dim3 grid(a.G * a.nct * a.nstrips, a.N);
   if (p.kernel == 0) {
-    auto kern = conv_s1_kernel<CPT, J>;
+    auto kern = conv_s1_kernel<CPT, J, MAXT>;
     QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     kern<<<grid, p.threads, p.smem, st>>>(a);
   } else {
-    auto kern = conv_roll_kernel<CPT, J>;
+    auto kern = conv_roll_kernel<CPT, J, MAXT>;
     QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     kern<<<grid, p.threads, p.smem, st>>>(a);
   }
@@ -328,15 +373,25 @@ int LaunchOne(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
   return 0;
 }
 
+template <int CPT, int J>
+int LaunchOne(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
+  if (p.threads <= 256) return LaunchBound<CPT, J, 256>(p, a, st);
+  if (p.threads <= 384) return LaunchBound<CPT, J, 384>(p, a, st);
+  return LaunchBound<CPT, J, 512>(p, a, st);
+}
+
 }  // namespace
 
 namespace qcnn {
 
-// Chooses the tiling of a conv layer.  Cost model (SM-cycles per image, lower is better):
-//   gather = lookups issued (incl. idle lanes / garbage columns) / 32 per clk
-//   build  = LUT entries built (incl. halo rows and per-channel-tile rebuilds) * (d_eff + 2) / 128 per clk
-// divided over the CTAs of one image and multiplied by the number of waves the whole batch needs on this GPU,
-// so small batches trade LUT rebuilds for parallelism and large batches do not.
+// Chooses the tiling of a conv layer for batch size N.  Cost model in SM-cycles per CTA, times the number of
+// waves the whole batch needs on this GPU (so small batches trade LUT rebuilds for parallelism):
+//   gather  = shared-memory wavefronts: one per (warp, tap, s, channel, position-slot) plus one 128-bit offset load
+//             per 4 channels -> (1 + 1/(4J)) per lookup slot, 1 wavefront / clk / SM
+//   build   = LUT entries built (incl. halo rows, garbage columns and per-channel-tile rebuilds) x
+//             (0.66 * dims + 0.3) issue slots / 32 lanes / ~2.5 warp-instructions per clk
+//   sync    = ~300 clk per (s [, input row]) phase pair
+// The two stages do not overlap inside a CTA (one CTA per SM), so the costs add.
 int PlanConv(qcnn_layer* L, int N) {
   if (L->plan_N == N) return 0;
   ConvPlan best;
@@ -345,7 +400,9 @@ int PlanConv(qcnn_layer* L, int N) {
   const int G = L->grp, Cg = L->Cin / G, Kg = L->Cout / G;
   const int taps = L->ksz * L->ksz;
   const size_t smemMax = L->ctx->smem_optin ? L->ctx->smem_optin : 227 * 1024;
-  const double dEff = std::min(L->d, Cg) <= 4 ? 4.0 : 8.0 * CeilDiv(std::min(L->d, Cg), 8);
+  double dimsSum = 0;  // sum over subspaces of the dims that exist
+  for (int s = 0; s < L->S; s++) dimsSum += std::max(0, std::min(Cg - s * L->d, L->d));
+  const double ipe = 0.66 * (dimsSum / L->S) + 0.3;  // issue slots per LUT entry
   const int cpts[2] = {32, 16};
   for (int ci = 0; ci < 2; ci++) {
     const int CPT = cpts[ci];
@@ -363,7 +420,8 @@ int PlanConv(qcnn_layer* L, int N) {
           a.R = R;
           a.nstrips = CeilDiv(L->Ho, R);
           a.CT = CT; a.nct = nct; a.cwarps = cwarps;
-          double lanesPerRow, builtPerStrip;
+          a.ksplit = 1;
+          double gatherSlots, builtEntries, phases;
           int warps;
           if (L->stride == 1) {
             p.kernel = 0;
@@ -375,8 +433,9 @@ int PlanConv(qcnn_layer* L, int N) {
             const int need2 = a.pwarps * 32 * J + (L->ksz - 1) * a.PW + (L->ksz - 1) + 1;
             a.PP = RoundUp(std::max(need1, need2), 4);
             warps = a.pwarps * cwarps;
-            lanesPerRow = static_cast<double>(a.pwarps) * 32 * J / R;  // lanes issued per output row
-            builtPerStrip = a.PP;
+            gatherSlots = static_cast<double>(a.pwarps) * J * taps * L->S * CT;   // wavefronts of LUT reads
+            builtEntries = static_cast<double>(a.PP) * L->K * L->S;
+            phases = L->S;
           } else {
             p.kernel = 1;
             a.rgroups = CeilDiv(L->ksz, L->stride);
@@ -387,32 +446,33 @@ int PlanConv(qcnn_layer* L, int N) {
             a.PP = RoundUp(a.PW * L->stride, 4);
             a.RI = 0;
             warps = a.pwarps * cwarps * a.rgroups;
-            lanesPerRow = static_cast<double>(a.pwarps) * 32 * J * (static_cast<double>(a.rgroups) * L->stride / L->ksz);
-            builtPerStrip = static_cast<double>(a.PP) * ((R - 1) * L->stride + L->ksz);  // positions x input rows
+            const double rowsIn = (R - 1) * L->stride + L->ksz;
+            gatherSlots = static_cast<double>(a.pwarps) * J * R * taps * L->S * CT;
+            builtEntries = static_cast<double>(a.PP) * L->K * L->S * rowsIn;
+            phases = L->S * rowsIn;
           }
           p.CPT = CPT; p.J = J;
           p.threads = warps * 32;
           if (p.threads > kMaxThreads || p.threads < 64) continue;
-          p.smem = sizeof(float) * (static_cast<size_t>(L->K) * a.PP + static_cast<size_t>(taps) * CT + L->K * 8);
+          p.smem = sizeof(float) * (static_cast<size_t>(L->K) * a.PP + static_cast<size_t>(taps) * CT +
+                                    16 * static_cast<size_t>(L->K) + 8 * static_cast<size_t>(a.PP));
           if (p.smem > smemMax) continue;
-          a.ksplit = 1;
-          while (a.ksplit * 2 <= L->K && a.PP * (a.ksplit * 2) <= p.threads && L->K % (a.ksplit * 2) == 0) a.ksplit *= 2;
-          // cost per image
-          const double rowsIssued = static_cast<double>(a.nstrips) * R;
-          const double gather = rowsIssued * lanesPerRow * taps * L->S * Kg * G / 32.0;
-          const double build = a.nstrips * builtPerStrip * L->K * L->S * (dEff + 2.0) * nct * G / 128.0;
-          // mild preference for more resident warps (latency hiding) and fewer, larger CTAs
-          const double occPenalty = warps < 8 ? 1.25 : (warps < 12 ? 1.08 : 1.0);
-          const double ctasPerImg = static_cast<double>(G) * nct * a.nstrips;
-          const double waves = std::ceil(ctasPerImg * N / L->ctx->sm_count);
-          const double cost = (gather + build) / ctasPerImg * waves * occPenalty;
+          const double gather = gatherSlots * (1.0 + 1.0 / (4.0 * J));
+          const double build = builtEntries * ipe / 32.0 / 2.5;
+          const double perCta = gather + build + 300.0 * phases;
+          // few resident warps cannot keep ~30 LDS in flight per SM; 64 accumulators at 512 threads spill
+          double occPenalty = warps < 6 ? 1.3 : (warps < 8 ? 1.1 : 1.0);
+          if (p.threads > 384 && J * CPT >= 64) occPenalty *= 1.1;
+          const double ctas = static_cast<double>(G) * nct * a.nstrips * N;
+          const double waves = std::ceil(ctas / L->ctx->sm_count);
+          const double cost = perCta * waves * occPenalty;
           if (cost < bestCost) { bestCost = cost; best = p; found = true; }
         }
       }
     }
   }
-  QCNN_CHECK(found, "qcnn_conv_layer_create: no tiling fits (Cout/grp=%d must be a multiple of 16; K=%d, k=%d, W=%d)",
-             Kg, L->K, L->ksz, L->Win);
+  QCNN_CHECK(found, "qcnn_conv_layer_create: no tiling fits (Cout/grp=%d must be a multiple of 16; K=%d must be a "
+             "multiple of 8; k=%d, W=%d)", Kg, L->K, L->ksz, L->Win);
   ConvArgs& a = best.a;
   a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
   a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = G; a.Cg = Cg; a.Kg = Kg;
@@ -439,6 +499,17 @@ int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
 #undef QCNN_DISPATCH
   if (rc == 0) L->ctx->launches++;
   return rc;
+}
+
+// human-readable tiling of the plan for batch N (bench / DESIGN bookkeeping)
+int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
+  if (int prc = PlanConv(L, N)) return prc;
+  const ConvPlan& p = L->plan;
+  snprintf(buf, cap, "%s CPT=%d J=%d threads=%d smem=%zuB grid=(%d,%d) R=%d strips=%d CT=%d nct=%d PP=%d pwarps=%d "
+           "cwarps=%d rgroups=%d", p.kernel == 0 ? "conv_s1" : "conv_roll", p.CPT, p.J, p.threads, p.smem,
+           p.a.G * p.a.nct * p.a.nstrips, N, p.a.R, p.a.nstrips, p.a.CT, p.a.nct, p.a.PP, p.a.pwarps, p.a.cwarps,
+           p.a.rgroups);
+  return 0;
 }
 
 }  // namespace qcnn

@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t Word(const uint4& v, int i) {
 // K: codewords per subspace; CPT: channels per thread; TN: images per CTA; PF: subspaces per chunk;
 // PRE: assignments stored as byte offsets (idx*4)
 template <int K, int CPT, int TN, int PF, bool PRE>
-__global__ void __launch_bounds__(kFcThreads) fc_aprx_kernel(const FcArgs a) {
+__global__ void __launch_bounds__(kFcThreads, 2) fc_aprx_kernel(const FcArgs a) {
   extern __shared__ __align__(16) float lut[];  // [TN][PF][K]
   using AV = typename AsmtVec<CPT>::type;
   const int tid = threadIdx.x;
@@ -85,27 +85,56 @@ __global__ void __launch_bounds__(kFcThreads) fc_aprx_kernel(const FcArgs a) {
         Zero(areg[r]);
       }
     }
-    // (2) build the LUT slice of this chunk: entry e = (nl*PF + r)*K + k
+    // (2) build the LUT slice of this chunk.  A thread owns (subspace r, codeword k) pairs: it loads the pair's
+    //     codebook row and source offsets once and sweeps the TN images (x loads are warp-broadcast).
     __syncthreads();  // the previous chunk's gather is done with `lut`
-    for (int e = tid; e < TN * PF * K; e += kFcThreads) {
-      const int k = e % K;
-      const int r = (e / K) % PF;
-      const int nl = e / (K * PF);
+    for (int pr = tid; pr < PF * K; pr += kFcThreads) {
+      const int k = pr % K;
+      const int r = pr / K;
       const int s = sc + r;
-      const int n = n0 + nl;
-      float v = 0.0f;
-      if (s < s_end && n < a.N) {
-        const int f0 = s * a.d;
-        const int sel = min(a.Din - f0, a.d);
-        const float* c = a.ctrd + (static_cast<size_t>(s) * K + k) * a.d;
-        const float* x = a.src + static_cast<size_t>(n) * a.Din;
-        for (int j = 0; j < sel; j++) {
-          const int f = f0 + j;
-          const int off = a.hw ? ((f % a.hw) * a.ch + f / a.hw) : f;  // NHWC source read in NCHW-flatten order
-          v = __fadd_rn(v, __fmul_rn(__ldg(x + off), __ldg(c + j)));
+      const int f0 = s * a.d;
+      const int sel = (s < s_end) ? min(a.Din - f0, a.d) : 0;
+      const float* crow = a.ctrd + (static_cast<size_t>(s) * K + k) * a.d;
+      if (a.d <= 8) {
+        float c[8];
+        int off[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          c[j] = 0.0f;
+          off[j] = 0;
+          if (j < sel) {
+            const int f = f0 + j;
+            off[j] = a.hw ? ((f % a.hw) * a.ch + f / a.hw) : f;  // NHWC source read in NCHW-flatten order
+            c[j] = __ldg(crow + j);
+          }
+        }
+#pragma unroll
+        for (int nl = 0; nl < TN; nl++) {
+          const int n = n0 + nl;
+          float v = 0.0f;
+          if (n < a.N) {
+            const float* x = a.src + static_cast<size_t>(n) * a.Din;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (j < sel) v = __fadd_rn(v, __fmul_rn(__ldg(x + off[j]), c[j]));
+          }
+          lut[(nl * PF + r) * K + k] = v;
+        }
+      } else {
+        for (int nl = 0; nl < TN; nl++) {
+          const int n = n0 + nl;
+          float v = 0.0f;
+          if (n < a.N) {
+            const float* x = a.src + static_cast<size_t>(n) * a.Din;
+            for (int j = 0; j < sel; j++) {
+              const int f = f0 + j;
+              const int off = a.hw ? ((f % a.hw) * a.ch + f / a.hw) : f;
+              v = __fadd_rn(v, __fmul_rn(__ldg(x + off), __ldg(crow + j)));
+            }
+          }
+          lut[(nl * PF + r) * K + k] = v;
         }
       }
-      lut[e] = v;
     }
     __syncthreads();
     // (3) gather-accumulate.  Rows past s_end hold zeros and index 0, so no tail guard is needed.
@@ -169,8 +198,8 @@ template <int K, bool PRE>
 int LaunchK(const FcArgs& a, int tn, dim3 grid, cudaStream_t st) {
   switch (tn) {
     case 1: return Launch<K, 16, 1, 16, PRE>(a, grid, st);
-    case 4: return Launch<K, 4, 4, (K <= 32 ? 32 : 16), PRE>(a, grid, st);
-    default: return Launch<K, 4, 8, (K <= 32 ? 32 : (K <= 64 ? 16 : 8)), PRE>(a, grid, st);
+    case 4: return Launch<K, 8, 4, (K <= 64 ? 16 : 8), PRE>(a, grid, st);
+    default: return Launch<K, 8, 8, 8, PRE>(a, grid, st);
   }
 }
 
@@ -181,8 +210,8 @@ namespace qcnn {
 // chunk length (subspaces) of the instantiation chosen for (K, tn) -- must mirror LaunchK above
 static int ChunkLen(int K, int tn) {
   if (tn == 1) return 16;
-  if (tn == 4) return K <= 32 ? 32 : 16;
-  return K <= 32 ? 32 : (K <= 64 ? 16 : 8);
+  if (tn == 4) return K <= 64 ? 16 : 8;
+  return 8;
 }
 
 int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st) {
@@ -199,7 +228,7 @@ int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaS
   // batch tile: 1 (latency path, 16 channels/thread, 128-bit loads), 4 or 8 images per CTA
   int tn = L->opt_fc_tn ? L->opt_fc_tn : (N >= 8 ? 8 : (N >= 4 ? 4 : 1));
   if (tn != 1 && tn != 4) tn = 8;
-  const int cpt = (tn == 1) ? 16 : 4;
+  const int cpt = (tn == 1) ? 16 : 8;
   const int pf = ChunkLen(L->K, tn);
   const int gx = CeilDiv(L->DoutPad, kFcThreads * cpt);
   const int gy = CeilDiv(N, tn);

@@ -67,6 +67,33 @@ void qcnn_ctx_destroy(qcnn_ctx* ctx) { delete ctx; }
 int qcnn_ctx_device(const qcnn_ctx* ctx) { return ctx ? ctx->device : -1; }
 int qcnn_ctx_sm_count(const qcnn_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
+int qcnn_dev_alloc(qcnn_ctx* ctx, size_t bytes, void** out) {
+  QCNN_CHECK(ctx && out, "qcnn_dev_alloc: NULL argument");
+  QCNN_CUDA(cudaSetDevice(ctx->device));
+  QCNN_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  return 0;
+}
+int qcnn_dev_free(qcnn_ctx* ctx, void* ptr) {
+  QCNN_CHECK(ctx, "qcnn_dev_free: NULL ctx");
+  if (ptr) QCNN_CUDA(cudaFree(ptr));
+  return 0;
+}
+int qcnn_copy_h2d(qcnn_ctx* ctx, void* dst, const void* src_h, size_t bytes, void* stream) {
+  QCNN_CHECK(ctx && dst && src_h, "qcnn_copy_h2d: NULL argument");
+  QCNN_CUDA(cudaMemcpyAsync(dst, src_h, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int qcnn_copy_d2h(qcnn_ctx* ctx, void* dst_h, const void* src, size_t bytes, void* stream) {
+  QCNN_CHECK(ctx && dst_h && src, "qcnn_copy_d2h: NULL argument");
+  QCNN_CUDA(cudaMemcpyAsync(dst_h, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int qcnn_stream_sync(qcnn_ctx* ctx, void* stream) {
+  QCNN_CHECK(ctx, "qcnn_stream_sync: NULL ctx");
+  QCNN_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 static qcnn_layer* NewLayer(qcnn_ctx* ctx, int kind) {
   qcnn_layer* L = new qcnn_layer();
   memset(static_cast<void*>(L), 0, sizeof(*L));
@@ -95,6 +122,7 @@ int qcnn_conv_layer_create(qcnn_ctx* ctx, int Cin, int Hin, int Win, int Cout, i
   QCNN_CHECK(grp >= 1 && Cin % grp == 0 && Cout % grp == 0, "qcnn_conv_layer_create: channels not divisible by grp");
   QCNN_CHECK(ksz >= 1 && stride >= 1 && pad >= 0 && pad < ksz, "qcnn_conv_layer_create: bad kernel geometry");
   QCNN_CHECK(Hin + 2 * pad >= ksz && Win + 2 * pad >= ksz, "qcnn_conv_layer_create: kernel larger than input");
+  QCNN_CHECK(K % 8 == 0, "qcnn_conv_layer_create: K=%d must be a multiple of 8 (LUT stage tiles 8 codewords)", K);
   const int taps = ksz * ksz;
   if (int rc = CheckPq("qcnn_conv_layer_create", S, K, d, asmt_h, static_cast<size_t>(Cout) * taps * S)) return rc;
   QCNN_CUDA(cudaSetDevice(ctx->device));
@@ -197,6 +225,13 @@ int qcnn_layer_set_param(qcnn_layer* L, const char* name, int value) {
   if (!strcmp(name, "fc_nsplit")) L->opt_fc_nsplit = value;
   else if (!strcmp(name, "fc_tn")) L->opt_fc_tn = value;
   else { SetError("qcnn_layer_set_param: unknown parameter '%s'", name); return 1; }
+  return 0;
+}
+
+int qcnn_layer_describe(qcnn_layer* L, int N, char* buf, size_t cap) {
+  QCNN_CHECK(L && buf && cap > 0 && N >= 1, "qcnn_layer_describe: bad argument");
+  if (L->kind == QCNN_KIND_CONV) return DescribeConv(L, N, buf, cap);
+  snprintf(buf, cap, "fc_aprx Din=%d Dout=%d S=%d K=%d d=%d", L->Din, L->Dout, L->S, L->K, L->d);
   return 0;
 }
 

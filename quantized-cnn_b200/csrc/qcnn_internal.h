@@ -116,6 +116,7 @@ struct qcnn_layer {
 namespace qcnn {
 
 int PlanConv(qcnn_layer* L, int N);
+int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap);
 int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st);
 int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st);
 

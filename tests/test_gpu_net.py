@@ -45,7 +45,8 @@ def test_alexnet_synthetic_weights_all_feature_maps(po, qcnn, ctx, synth_dir):
     # (a) un-fused: every featMapLst entry is materialised and compared
     net.set_keep_maps(True)
     logits = torch.empty((N, 1000), dtype=torch.float32, device="cuda")
-    prob = net.forward(imgd, logits=logits).cpu().numpy()
+    prob_d = net.forward(imgd, logits=logits)   # keep alive: featMapLst[23] lives in this caller-owned tensor
+    prob = prob_d.cpu().numpy()
     for l in range(24):
         fm = net.featmap(l, N)
         assert fm is not None, l

@@ -1,0 +1,36 @@
+"""Minimal driver for ncu captures: builds the AlexNet PQ net and runs `--iters` forward passes at batch `--batch`.
+    ncu --set full --clock-control none --import-source on -k regex:'conv_|fc_aprx' -s <skip> -c <n> -o out \
+        python tools/profile_step.py --batch 256 --iters 2
+"""
+import argparse
+import importlib
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=2)
+    args = ap.parse_args()
+    import torch
+    q = importlib.import_module("quantized-cnn_b200")
+    tmp = tempfile.mkdtemp(prefix="qcnn_prof_")
+    d, pfx, what = bench.model_files(q, tmp)
+    ctx = q.Context(0)
+    net = q.Net(ctx, d, pfx, "AlexNet")
+    img = torch.from_numpy(bench.lcg_images(args.batch, 12345)).cuda()
+    prob = torch.empty((args.batch, 1000), dtype=torch.float32, device="cuda")
+    for _ in range(args.iters):
+        net.forward(img, prob=prob)
+    torch.cuda.synchronize()
+    print("done", what, float(prob[0].max()))
+
+
+if __name__ == "__main__":
+    main()

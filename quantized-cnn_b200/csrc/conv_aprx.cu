@@ -35,24 +35,69 @@ namespace {
 constexpr int kMaxThreads = 512;
 
 // ------------------------------------------------------------------------------------------------------------
-// staging helpers
+// Operand staging.  Everything the LUT stage of subspace s+1 needs from global memory (input pixels of the
+// subspace's channels, its codebook rows, its assignment slice) is copied ASYNCHRONOUSLY (cp.async, no registers)
+// into shared-memory staging buffers right before the gather of subspace s starts, and picked up after it ends,
+// so no global-load latency is exposed between the two stages.
 // ------------------------------------------------------------------------------------------------------------
-// cb2[jj][k] = (c, c) with c = ctrd[s][k][jc + jj]  (zero beyond the subspace's real dims)
-__device__ __forceinline__ void StageCodebook(float2* __restrict__ cb2, const float* __restrict__ ctrd, int s, int K,
+__device__ __forceinline__ void CpAsync4(void* smemDst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smemDst));
+  const int sz = valid ? 4 : 0;  // src-size 0: nothing is read, the 4 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void CpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// raw codebook chunk: cbN[k*8 + jj] <- ctrd[s][k][jc + jj]   (zero beyond the subspace's real dims)
+__device__ __forceinline__ void FetchCodebook(float* __restrict__ cbN, const float* __restrict__ ctrd, int s, int K,
                                               int d, int jc, int nj, int tid, int T) {
+  const float* base = ctrd + static_cast<size_t>(s) * K * d + jc;
   for (int e = tid; e < K * 8; e += T) {
     const int k = e >> 3, jj = e & 7;
-    const float c = (jj < nj) ? __ldg(ctrd + (static_cast<size_t>(s) * K + k) * d + jc + jj) : 0.0f;
-    cb2[jj * K + k] = make_float2(c, c);
+    CpAsync4(cbN + e, base + (jj < nj ? k * d + jj : 0), jj < nj);
+  }
+}
+// cb2[jj][k] = (c, c)
+__device__ __forceinline__ void CommitCodebook(const float* __restrict__ cbN, float2* __restrict__ cb2, int K, int tid,
+                                               int T) {
+  for (int e = tid; e < K * 8; e += T) {
+    const float c = cbN[e];
+    cb2[(e & 7) * K + (e >> 3)] = make_float2(c, c);
   }
 }
 
-// idx[tap][c] = asmt[tap][c] * (PP * 4)  -> byte offset of LUT row k
-__device__ __forceinline__ void StageOffsets(uint32_t* __restrict__ idx, const uint8_t* __restrict__ ap, int taps,
-                                             int CT, int KgPad, uint32_t rowBytes, int tid, int T) {
-  for (int e = tid; e < taps * CT; e += T) {
-    const int tap = e / CT, c = e - tap * CT;
-    idx[e] = static_cast<uint32_t>(__ldg(ap + tap * KgPad + c)) * rowBytes;
+// raw assignment slice of (group, s, channel tile): idN[tap*CT + c] (bytes), fetched as 4-channel words
+__device__ __forceinline__ void FetchOffsets(uint8_t* __restrict__ idN, const uint8_t* __restrict__ ap, int taps,
+                                             int CT, int KgPad, int tid, int T) {
+  const int wpt = CT >> 2;
+  for (int w = tid; w < taps * wpt; w += T) {
+    const int tap = w / wpt, c4 = w - tap * wpt;
+    CpAsync4(idN + 4 * w, ap + static_cast<size_t>(tap) * KgPad + 4 * c4, true);
+  }
+}
+// idx[tap][c] = asmt * (PP * 4): byte offset of LUT row k
+__device__ __forceinline__ void CommitOffsets(const uint8_t* __restrict__ idN, uint32_t* __restrict__ idx, int taps,
+                                              int CT, uint32_t rowBytes, int tid, int T) {
+  const int wpt = CT >> 2;
+  for (int w = tid; w < taps * wpt; w += T) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(idN + 4 * w);
+    *reinterpret_cast<uint4*>(idx + 4 * w) = make_uint4((v & 0xFFu) * rowBytes, ((v >> 8) & 0xFFu) * rowBytes,
+                                                        ((v >> 16) & 0xFFu) * rowBytes, (v >> 24) * rowBytes);
+  }
+}
+
+// input pixels: xs[jj][pos] <- channel ch0+jj of the pixel behind LUT position pos; posoff[pos] = element offset
+// of the pixel's channel 0 (or -1 for zero padding); chStride = 1 for NHWC, H*W for NCHW
+__device__ __forceinline__ void FetchPixels(float* __restrict__ xs, const float* __restrict__ src,
+                                            const int* __restrict__ posoff, int PP, int ch0, size_t chStride, int nj,
+                                            int tid, int T) {
+  for (int pos = tid; pos < PP; pos += T) {
+    const int off = posoff[pos];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      const bool ok = off >= 0 && jj < nj;
+      CpAsync4(xs + jj * PP + pos, src + (ok ? off + (ch0 + jj) * chStride : 0), ok);
+    }
   }
 }
 
@@ -60,6 +105,22 @@ __device__ __forceinline__ void StageOffsets(uint32_t* __restrict__ idx, const u
 // LUT stage: lut[k][p] (+)= sum_{jj<nj} cb[jj][k] * xs[jj][p], tile of 8 codewords x 4 positions per thread.
 // Lanes walk the position tiles (128-bit LUT stores and x loads are conflict-free, codebook loads broadcast).
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void LutStep(float2 (&acc)[8][2], const float2* __restrict__ cb2, const float* __restrict__ xs,
+                                        int K, int PP, int j, int k0, int p0) {
+  const float4 xv = *reinterpret_cast<const float4*>(xs + j * PP + p0);
+  const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
+  const float4* cp = reinterpret_cast<const float4*>(cb2 + j * K + k0);
+#pragma unroll
+  for (int kk = 0; kk < 4; kk++) {
+    const float4 cc = cp[kk];  // (c[2kk], c[2kk], c[2kk+1], c[2kk+1])
+    const float2 ca = make_float2(cc.x, cc.y), cb = make_float2(cc.z, cc.w);
+    acc[2 * kk][0] = __ffma2_rn(ca, x01, acc[2 * kk][0]);
+    acc[2 * kk][1] = __ffma2_rn(ca, x23, acc[2 * kk][1]);
+    acc[2 * kk + 1][0] = __ffma2_rn(cb, x01, acc[2 * kk + 1][0]);
+    acc[2 * kk + 1][1] = __ffma2_rn(cb, x23, acc[2 * kk + 1][1]);
+  }
+}
+
 __device__ __forceinline__ void BuildLut(float* __restrict__ lut, const float2* __restrict__ cb2,
                                          const float* __restrict__ xs, int K, int PP, int nj, bool first, int tid,
                                          int T) {
@@ -81,20 +142,12 @@ __device__ __forceinline__ void BuildLut(float* __restrict__ lut, const float2* 
         acc[k][1] = make_float2(v.z, v.w);
       }
     }
+    if (nj == 8) {  // two steps in flight: enough ILP to cover the LDS latency without blowing the register file
 #pragma unroll 2
-    for (int j = 0; j < nj; j++) {
-      const float4 xv = *reinterpret_cast<const float4*>(xs + j * PP + p0);
-      const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
-      const float4* cp = reinterpret_cast<const float4*>(cb2 + j * K + k0);
-#pragma unroll
-      for (int kk = 0; kk < 4; kk++) {
-        const float4 cc = cp[kk];  // (c[2kk], c[2kk], c[2kk+1], c[2kk+1])
-        const float2 ca = make_float2(cc.x, cc.y), cb = make_float2(cc.z, cc.w);
-        acc[2 * kk][0] = __ffma2_rn(ca, x01, acc[2 * kk][0]);
-        acc[2 * kk][1] = __ffma2_rn(ca, x23, acc[2 * kk][1]);
-        acc[2 * kk + 1][0] = __ffma2_rn(cb, x01, acc[2 * kk + 1][0]);
-        acc[2 * kk + 1][1] = __ffma2_rn(cb, x23, acc[2 * kk + 1][1]);
-      }
+      for (int j = 0; j < 8; j++) LutStep(acc, cb2, xs, K, PP, j, k0, p0);
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < nj; j++) LutStep(acc, cb2, xs, K, PP, j, k0, p0);
     }
 #pragma unroll
     for (int k = 0; k < 8; k++)
@@ -164,9 +217,12 @@ __device__ __forceinline__ void StoreChannels(float* __restrict__ out, const Acc
 
 struct SmemLayout {
   float* lut;      // [K][PP]
-  uint32_t* idx;   // [taps][CT]
-  float2* cb2;     // [8][K]
-  float* xs;       // [8][PP]
+  uint32_t* idx;   // [taps][CT]   LUT row byte offsets of the current subspace
+  float2* cb2;     // [8][K]       duplicated codebook chunk of the current subspace
+  float* xs[2];    // [8][PP]      input pixels, double-buffered (current / next subspace)
+  int* posoff;     // [PP]
+  float* cbN;      // [K*8]        raw codebook chunk of the next subspace (cp.async target)
+  uint8_t* idN;    // [taps*CT]    raw assignment slice of the next subspace (cp.async target)
 };
 
 __device__ __forceinline__ SmemLayout Carve(unsigned char* smem, int K, int PP, int taps, int CT) {
@@ -174,8 +230,23 @@ __device__ __forceinline__ SmemLayout Carve(unsigned char* smem, int K, int PP, 
   s.lut = reinterpret_cast<float*>(smem);
   s.idx = reinterpret_cast<uint32_t*>(s.lut + static_cast<size_t>(K) * PP);
   s.cb2 = reinterpret_cast<float2*>(s.idx + taps * CT);
-  s.xs = reinterpret_cast<float*>(s.cb2 + 8 * K);
+  s.xs[0] = reinterpret_cast<float*>(s.cb2 + 8 * K);
+  s.xs[1] = s.xs[0] + 8 * PP;
+  s.posoff = reinterpret_cast<int*>(s.xs[1] + 8 * PP);
+  s.cbN = reinterpret_cast<float*>(s.posoff + PP);
+  s.idN = reinterpret_cast<uint8_t*>(s.cbN + 8 * K);
   return s;
+}
+
+// stage one (s, jc) chunk with exposed latency: only for the rare jc > 0 chunks of subspaces wider than 8 dims
+__device__ __forceinline__ void StageChunkDirect(const SmemLayout& sm, float* xs, const ConvArgs& a, const float* src,
+                                                 int s, int jc, int nj, int ch0, size_t chStride, int tid, int T) {
+  FetchCodebook(sm.cbN, a.ctrd, s, a.K, a.d, jc, nj, tid, T);
+  FetchPixels(xs, src, sm.posoff, a.PP, ch0, chStride, nj, tid, T);
+  CpAsyncCommit();
+  CpAsyncWaitAll();
+  __syncthreads();
+  CommitCodebook(sm.cbN, sm.cb2, a.K, tid, T);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -200,6 +271,20 @@ __global__ void __launch_bounds__(MAXT, 1) conv_s1_kernel(const ConvArgs a) {
   const int hin0 = r0 - a.pad;           // input row held at ri = 0
   const int q0 = pw * 32 * J + lane;     // first flat position of this thread (others at +32 j)
   const int cbase = ct * a.CT + cw * CPT;  // first channel (within the group) of this thread
+  const float* src = a.src + static_cast<size_t>(n) * a.Hi * a.Wi * a.Cin + g * a.Cg;
+  const uint8_t* asmtG = a.asmt + static_cast<size_t>(g) * a.S * taps * a.KgPad + ct * a.CT;
+
+  // LUT position -> source pixel (NHWC element offset within this image/group), -1 = zero padding
+  for (int pos = tid; pos < a.PP; pos += T) {
+    int off = -1;
+    const int pp = pos - a.pad;
+    if (pp >= 0) {
+      const int ri = pp / a.PW, wi = pp - ri * a.PW;
+      const int hi = hin0 + ri;
+      if (ri < a.RI && wi < a.Wi && hi >= 0 && hi < a.Hi) off = (hi * a.Wi + wi) * a.Cin;
+    }
+    sm.posoff[pos] = off;
+  }
 
   Acc<CPT, J> acc;
   {
@@ -208,36 +293,41 @@ __global__ void __launch_bounds__(MAXT, 1) conv_s1_kernel(const ConvArgs a) {
     for (int c = 0; c < CPT; c++) bv[c] = __ldg(a.bias + g * a.Kg + cbase + c);
     acc.Fill(bv);
   }
+  __syncthreads();  // posoff visible
 
   const uint32_t rowBytes = static_cast<uint32_t>(a.PP) * 4u;
+  {
+    const int nj0 = max(0, min(8, min(a.Cg, a.d)));
+    FetchCodebook(sm.cbN, a.ctrd, 0, a.K, a.d, 0, nj0, tid, T);
+    FetchOffsets(sm.idN, asmtG, taps, a.CT, a.KgPad, tid, T);
+    FetchPixels(sm.xs[0], src, sm.posoff, a.PP, 0, 1, nj0, tid, T);
+    CpAsyncCommit();
+  }
   for (int s = 0; s < a.S; s++) {
     const int dsel = min(a.Cg - s * a.d, a.d);  // dims of this subspace that exist (reference CaffeEva.cc:1277)
+    float* xs = sm.xs[s & 1];
     // ---- LUT stage ----
-    for (int jc = 0; jc == 0 || jc < dsel; jc += 8) {
-      const int nj = max(0, min(8, dsel - jc));
-      __syncthreads();  // previous gather / previous chunk is done with lut, idx, cb2, xs
-      StageCodebook(sm.cb2, a.ctrd, s, a.K, a.d, jc, nj, tid, T);
-      if (jc == 0)
-        StageOffsets(sm.idx, a.asmt + (static_cast<size_t>(g) * a.S + s) * taps * a.KgPad + ct * a.CT, taps, a.CT,
-                     a.KgPad, rowBytes, tid, T);
-      // xs[jj][pos]: input channel (g*Cg + s*d + jc + jj) at LUT position pos, 0 for padding
-      for (int e = tid; e < a.PP * 8; e += T) {
-        const int jj = e / a.PP;
-        const int pos = e - jj * a.PP;
-        float x = 0.0f;
-        const int pp = pos - a.pad;
-        if (jj < nj && pp >= 0) {
-          const int ri = pp / a.PW, wi = pp - ri * a.PW;
-          const int hi = hin0 + ri;
-          if (ri < a.RI && wi < a.Wi && hi >= 0 && hi < a.Hi)
-            x = __ldg(a.src + ((static_cast<size_t>(n) * a.Hi + hi) * a.Wi + wi) * a.Cin + g * a.Cg + s * a.d + jc + jj);
-        }
-        sm.xs[e] = x;
-      }
+    CpAsyncWaitAll();
+    __syncthreads();  // (A) staged operands of s have landed; the previous gather is done with lut / idx
+    CommitCodebook(sm.cbN, sm.cb2, a.K, tid, T);
+    CommitOffsets(sm.idN, sm.idx, taps, a.CT, rowBytes, tid, T);
+    __syncthreads();  // (B)
+    BuildLut(sm.lut, sm.cb2, xs, a.K, a.PP, max(0, min(8, dsel)), true, tid, T);
+    for (int jc = 8; jc < dsel; jc += 8) {
+      const int nj = min(8, dsel - jc);
       __syncthreads();
-      BuildLut(sm.lut, sm.cb2, sm.xs, a.K, a.PP, nj, jc == 0, tid, T);
+      StageChunkDirect(sm, xs, a, src, s, jc, nj, s * a.d + jc, 1, tid, T);
+      __syncthreads();
+      BuildLut(sm.lut, sm.cb2, xs, a.K, a.PP, nj, false, tid, T);
     }
-    __syncthreads();
+    __syncthreads();  // (C) lut complete; cbN / idN / the other xs buffer are free
+    if (s + 1 < a.S) {  // operands of the next subspace fly in while this one is gathered
+      const int njn = max(0, min(8, min(a.Cg - (s + 1) * a.d, a.d)));
+      FetchCodebook(sm.cbN, a.ctrd, s + 1, a.K, a.d, 0, njn, tid, T);
+      FetchOffsets(sm.idN, asmtG + static_cast<size_t>(s + 1) * taps * a.KgPad, taps, a.CT, a.KgPad, tid, T);
+      FetchPixels(sm.xs[(s + 1) & 1], src, sm.posoff, a.PP, (s + 1) * a.d, 1, njn, tid, T);
+      CpAsyncCommit();
+    }
     // ---- gather stage ----
     const char* lutq = reinterpret_cast<const char*>(sm.lut) + q0 * 4;
     const uint32_t* ip = sm.idx + cw * CPT;
@@ -285,6 +375,19 @@ __global__ void __launch_bounds__(MAXT, 1) conv_roll_kernel(const ConvArgs a) {
   const int PH = a.PW;
   const int wo0 = pw * 32 * J + lane;
   const int cbase = ct * a.CT + cw * CPT;
+  // source addressing: pixel (hi, wi), channel ch  ->  base + hi*rowStride + wi*pixStride + ch*chStride
+  const size_t chStride = a.src_nchw ? static_cast<size_t>(a.Hi) * a.Wi : 1;
+  const int pixStride = a.src_nchw ? 1 : a.Cin;
+  const size_t rowStride = static_cast<size_t>(a.Wi) * pixStride;
+  const float* src = a.src + static_cast<size_t>(n) * a.Hi * a.Wi * a.Cin + static_cast<size_t>(g) * a.Cg * chStride;
+  const uint8_t* asmtG = a.asmt + static_cast<size_t>(g) * a.S * taps * a.KgPad + ct * a.CT;
+
+  // LUT position (phase-major de-interleaved column) -> element offset of the pixel inside its input row
+  for (int pos = tid; pos < a.PP; pos += T) {
+    const int phase = pos / PH, i = pos - phase * PH;
+    const int wi = i * a.stride + phase - a.pad;
+    sm.posoff[pos] = (phase < a.stride && wi >= 0 && wi < a.Wi) ? wi * pixStride : -1;
+  }
 
   float bias[CPT];
 #pragma unroll
@@ -292,56 +395,78 @@ __global__ void __launch_bounds__(MAXT, 1) conv_roll_kernel(const ConvArgs a) {
   Acc<CPT, J> acc;
   acc.Fill(bias);
   int ho_cur = ho0 + rg;  // output row this warp is accumulating
+  __syncthreads();        // posoff visible
 
   const uint32_t rowBytes = static_cast<uint32_t>(a.PP) * 4u;
   const int hi_begin = ho0 * a.stride - a.pad;
   const int hi_end = (ho_end - 1) * a.stride - a.pad + a.ksz;
-  bool idx_ready = false;
-  for (int hi = hi_begin; hi < hi_end; hi++) {
-    const bool row_valid = hi >= 0 && hi < a.Hi;   // CTA-uniform; rows outside the image contribute nothing
+  const int hi_lo = max(hi_begin, 0), hi_hi = min(hi_end, a.Hi);  // rows outside the image contribute nothing
+  const int steps = (hi_hi - hi_lo) * a.S;                         // (input row, subspace) pairs, row-major
+
+  if (steps > 0) {
+    const int nj0 = max(0, min(8, min(a.Cg, a.d)));
+    FetchCodebook(sm.cbN, a.ctrd, 0, a.K, a.d, 0, nj0, tid, T);
+    FetchOffsets(sm.idN, asmtG, taps, a.CT, a.KgPad, tid, T);
+    FetchPixels(sm.xs[0], src + hi_lo * rowStride, sm.posoff, a.PP, 0, chStride, nj0, tid, T);
+    CpAsyncCommit();
+  }
+  int hi = hi_lo, s = 0;
+  for (int it = 0; it < steps; it++) {
+    const int dsel = min(a.Cg - s * a.d, a.d);
     const int kh = hi + a.pad - ho_cur * a.stride;  // warp-uniform
-    const bool active = row_valid && ho_cur < ho_end && kh >= 0 && kh < a.ksz;
-    if (row_valid) {
-      for (int s = 0; s < a.S; s++) {
-        const int dsel = min(a.Cg - s * a.d, a.d);
-        for (int jc = 0; jc == 0 || jc < dsel; jc += 8) {
-          const int nj = max(0, min(8, dsel - jc));
-          __syncthreads();
-          StageCodebook(sm.cb2, a.ctrd, s, a.K, a.d, jc, nj, tid, T);
-          if (jc == 0 && (a.S > 1 || !idx_ready)) {
-            StageOffsets(sm.idx, a.asmt + (static_cast<size_t>(g) * a.S + s) * taps * a.KgPad + ct * a.CT, taps, a.CT,
-                         a.KgPad, rowBytes, tid, T);
-            idx_ready = true;
-          }
-          for (int e = tid; e < a.PP * 8; e += T) {
-            const int jj = e / a.PP;
-            const int pos = e - jj * a.PP;
-            const int phase = pos / PH, i = pos - phase * PH;
-            const int wi = i * a.stride + phase - a.pad;
-            float x = 0.0f;
-            if (jj < nj && phase < a.stride && wi >= 0 && wi < a.Wi) {
-              const int ch = g * a.Cg + s * a.d + jc + jj;
-              x = a.src_nchw ? __ldg(a.src + ((static_cast<size_t>(n) * a.Cin + ch) * a.Hi + hi) * a.Wi + wi)
-                             : __ldg(a.src + ((static_cast<size_t>(n) * a.Hi + hi) * a.Wi + wi) * a.Cin + ch);
-            }
-            sm.xs[e] = x;
-          }
-          __syncthreads();
-          BuildLut(sm.lut, sm.cb2, sm.xs, a.K, a.PP, nj, jc == 0, tid, T);
-        }
-        __syncthreads();
-        if (active) {
-          const char* lutq = reinterpret_cast<const char*>(sm.lut) + wo0 * 4;
-          const uint32_t* ip = sm.idx + (kh * a.ksz) * a.CT + cw * CPT;
-          for (int kw = 0; kw < a.ksz; kw++) {
-            const int phase = kw % a.stride, sh = kw / a.stride;
-            GatherTap<CPT, J>(acc, lutq + (phase * PH + sh) * 4, ip);
-            ip += a.CT;
-          }
-        }
+    const bool active = ho_cur < ho_end && kh >= 0 && kh < a.ksz;
+    float* xs = sm.xs[it & 1];
+    CpAsyncWaitAll();
+    __syncthreads();  // (A)
+    CommitCodebook(sm.cbN, sm.cb2, a.K, tid, T);
+    if (a.S > 1 || it == 0) CommitOffsets(sm.idN, sm.idx, taps, a.CT, rowBytes, tid, T);
+    __syncthreads();  // (B)
+    BuildLut(sm.lut, sm.cb2, xs, a.K, a.PP, max(0, min(8, dsel)), true, tid, T);
+    for (int jc = 8; jc < dsel; jc += 8) {
+      const int nj = min(8, dsel - jc);
+      __syncthreads();
+      StageChunkDirect(sm, xs, a, src + hi * rowStride, s, jc, nj, s * a.d + jc, chStride, tid, T);
+      __syncthreads();
+      BuildLut(sm.lut, sm.cb2, xs, a.K, a.PP, nj, false, tid, T);
+    }
+    __syncthreads();  // (C)
+    // next (row, subspace)
+    int hin = hi, sn = s + 1;
+    if (sn == a.S) { sn = 0; hin = hi + 1; }
+    if (it + 1 < steps) {
+      const int njn = max(0, min(8, min(a.Cg - sn * a.d, a.d)));
+      FetchCodebook(sm.cbN, a.ctrd, sn, a.K, a.d, 0, njn, tid, T);
+      if (a.S > 1) FetchOffsets(sm.idN, asmtG + static_cast<size_t>(sn) * taps * a.KgPad, taps, a.CT, a.KgPad, tid, T);
+      FetchPixels(sm.xs[(it + 1) & 1], src + hin * rowStride, sm.posoff, a.PP, sn * a.d, chStride, njn, tid, T);
+      CpAsyncCommit();
+    }
+    if (active) {
+      const char* lutq = reinterpret_cast<const char*>(sm.lut) + wo0 * 4;
+      const uint32_t* ip = sm.idx + (kh * a.ksz) * a.CT + cw * CPT;
+      for (int kw = 0; kw < a.ksz; kw++) {
+        const int phase = kw % a.stride, sh = kw / a.stride;
+        GatherTap<CPT, J>(acc, lutq + (phase * PH + sh) * 4, ip);
+        ip += a.CT;
       }
     }
     // this input row was the last one the current output row needs: emit it and move on
+    if (s == a.S - 1 && ho_cur < ho_end && kh == a.ksz - 1) {
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        const int wo = wo0 + 32 * j;
+        if (wo < a.Wo) {
+          float* out = a.dst + ((static_cast<size_t>(n) * a.Ho + ho_cur) * a.Wo + wo) * a.Cout + g * a.Kg + cbase;
+          StoreChannels<CPT, J>(out, acc, j, a.relu);
+        }
+      }
+      acc.Fill(bias);
+      ho_cur += a.rgroups;
+    }
+    hi = hin; s = sn;
+  }
+  // output rows whose window ends below the image (padding rows were skipped above)
+  for (int h = max(hi_hi, hi_begin); h < hi_end; h++) {
+    const int kh = h + a.pad - ho_cur * a.stride;
     if (ho_cur < ho_end && kh == a.ksz - 1) {
 #pragma unroll
       for (int j = 0; j < J; j++) {
@@ -454,12 +579,15 @@ int PlanConv(qcnn_layer* L, int N) {
           p.CPT = CPT; p.J = J;
           p.threads = warps * 32;
           if (p.threads > kMaxThreads || p.threads < 64) continue;
+          // lut + idx + cb2 + xs[2] + posoff + cbN (floats) + idN (bytes)
           p.smem = sizeof(float) * (static_cast<size_t>(L->K) * a.PP + static_cast<size_t>(taps) * CT +
-                                    16 * static_cast<size_t>(L->K) + 8 * static_cast<size_t>(a.PP));
+                                    24 * static_cast<size_t>(L->K) + 17 * static_cast<size_t>(a.PP)) +
+                   RoundUp(taps * CT, 16);
           if (p.smem > smemMax) continue;
-          const double gather = gatherSlots * (1.0 + 1.0 / (4.0 * J));
-          const double build = builtEntries * ipe / 32.0 / 2.5;
-          const double perCta = gather + build + 300.0 * phases;
+          // measured on B200 (profiles/): ~1.3 clk per gather wavefront, ~0.12 clk per LUT entry at d = 8
+          const double gather = gatherSlots * (1.0 + 1.0 / (4.0 * J)) * 1.3;
+          const double build = builtEntries * ipe / 5.5 * 0.12;
+          const double perCta = gather + build + 400.0 * phases;
           // few resident warps cannot keep ~30 LDS in flight per SM; 64 accumulators at 512 threads spill
           double occPenalty = warps < 6 ? 1.3 : (warps < 8 ? 1.1 : 1.0);
           if (p.threads > 384 && J * CPT >= 64) occPenalty *= 1.1;

@@ -89,22 +89,66 @@ __global__ void lrn_maxpool_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
+// 8 consecutive channels of one pixel at once: the squared/scaled window terms are computed once and shared by the
+// 8 sliding sums (same per-output operation order as LrnAt / the reference).  C % 4 == 0, c0 % 8 == 0.
+template <int SIZE>
+__device__ __forceinline__ void LrnChunk8(const float* __restrict__ px, int c0, int C, float coeff, float kini,
+                                          float nbeta, float (&out)[8]) {
+  constexpr int RAD = (SIZE - 1) / 2;
+  constexpr int LO = (RAD + 3) / 4 * 4;        // floats loaded below c0 (multiple of 4 so 128-bit loads stay aligned)
+  constexpr int NV = (LO + 8 + LO) / 4;        // float4 loads
+  float x[NV * 4];
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    const int cc = c0 - LO + 4 * v;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cc >= 0 && cc < C) q = __ldg(reinterpret_cast<const float4*>(px + cc));
+    x[4 * v] = q.x; x[4 * v + 1] = q.y; x[4 * v + 2] = q.z; x[4 * v + 3] = q.w;
+  }
+  float t[8 + 2 * RAD];
+#pragma unroll
+  for (int i = 0; i < 8 + 2 * RAD; i++) {
+    const float v = x[LO - RAD + i];
+    t[i] = __fmul_rn(__fmul_rn(v, v), coeff);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    float sum = kini;
+#pragma unroll
+    for (int w = 0; w < SIZE; w++) sum = __fadd_rn(sum, t[c + w]);
+    out[c] = __fmul_rn(x[LO + c], expf(__fmul_rn(nbeta, logf(sum))));
+  }
+}
+
 // Tiled variant: one CTA per (image, output row).  The <= ksz input rows the row needs are normalised ONCE into
 // shared memory and then pooled, so the expf/logf pair runs ~ksz/stride times per input element instead of
 // ksz^2/stride^2 times, and the normalised map still never reaches HBM.
+template <int SIZE>
 __global__ void lrn_maxpool_tiled_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int C,
                                          int Ho, int Wo, int size, float coeff, float kini, float nbeta, int ksz,
                                          int pad, int stride) {
   extern __shared__ float tile[];  // [rows][W][C]
-  const int rad = (size - 1) / 2;
   const int ho = blockIdx.x, n = blockIdx.y;
   const int hL = max(0, ho * stride - pad), hU = min(H, ho * stride + ksz - pad) - 1;
   const int rows = hU - hL + 1;
   const int rowLen = W * C;
   const float* base = src + (static_cast<size_t>(n) * H + hL) * rowLen;
-  for (int e = threadIdx.x; e < rows * rowLen; e += blockDim.x) {
-    const int p = e / C, c = e - p * C;
-    tile[e] = LrnAt(base + static_cast<size_t>(p) * C, c, C, size, rad, coeff, kini, nbeta);
+  if (SIZE > 0) {
+    const int cpp = C >> 3;  // 8-channel chunks per pixel
+    for (int e = threadIdx.x; e < rows * W * cpp; e += blockDim.x) {
+      const int p = e / cpp, c0 = (e - p * cpp) << 3;
+      float o[8];
+      LrnChunk8<(SIZE > 0 ? SIZE : 1)>(base + static_cast<size_t>(p) * C, c0, C, coeff, kini, nbeta, o);
+      float4* tp = reinterpret_cast<float4*>(tile + static_cast<size_t>(p) * C + c0);
+      tp[0] = make_float4(o[0], o[1], o[2], o[3]);
+      tp[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  } else {
+    const int rad = (size - 1) / 2;
+    for (int e = threadIdx.x; e < rows * rowLen; e += blockDim.x) {
+      const int p = e / C, c = e - p * C;
+      tile[e] = LrnAt(base + static_cast<size_t>(p) * C, c, C, size, rad, coeff, kini, nbeta);
+    }
   }
   __syncthreads();
   float* out = dst + (static_cast<size_t>(n) * Ho + ho) * Wo * C;
@@ -219,7 +263,8 @@ int LaunchLrnMaxPool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, 
   const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
   const size_t tileBytes = sizeof(float) * static_cast<size_t>(ksz) * W * C;
   if (tileBytes <= 160 * 1024 && N <= 65535) {
-    auto kern = lrn_maxpool_tiled_kernel;
+    // specialised 8-channel path for the 5-wide window every reference table uses (CaffePara.cc:31,35,...)
+    auto kern = (size == 5 && C % 8 == 0) ? lrn_maxpool_tiled_kernel<5> : lrn_maxpool_tiled_kernel<0>;
     if (tileBytes > 48 * 1024)
       QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileBytes));
     kern<<<dim3(Ho, N), kThreads, tileBytes, st>>>(src, dst, H, W, C, Ho, Wo, size, alpha / size, k, -beta, ksz, pad,

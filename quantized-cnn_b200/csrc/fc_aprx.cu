@@ -6,8 +6,10 @@
 // Mapping (HBM/L2 stream of the assignment matrix is the only large operand):
 //   * lane = output channel.  A thread owns CPT consecutive channels and TN images -> TN*CPT accumulators.
 //   * the device assignment table is [S][DoutPad] bytes, so a warp reads 32*CPT contiguous bytes per subspace
-//     row (128-bit loads at CPT=16); rows of one chunk (PF subspaces) are prefetched into registers BEFORE the
-//     chunk's LUT slice is built, so the HBM stream overlaps the LUT arithmetic.
+//     row (128-bit loads at CPT=16); rows stream through a rolling register window (one block of 8 rows in flight
+//     while the previous block is consumed), the first block being issued BEFORE the chunk's LUT slice is built,
+//     so the HBM/L2 stream overlaps the LUT arithmetic;
+//   * the input slice and codebook rows of chunk c+1 are staged by cp.async while chunk c is gathered.
 //   * the LUT slice of the chunk ([TN][PF][K] floats) lives in shared memory.  With K <= 32 one LUT row is
 //     <= 128 B = one bank sweep: distinct codewords hit distinct banks and equal codewords broadcast, so the
 //     lane-dependent gather is bank-conflict free by construction.
@@ -51,12 +53,42 @@ __device__ __forceinline__ uint32_t Word(const uint4& v, int i) {
   return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
 
-// K: codewords per subspace; CPT: channels per thread; TN: images per CTA; PF: subspaces per chunk;
+__device__ __forceinline__ void CpAsync4(void* smemDst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smemDst));
+  const int sz = valid ? 4 : 0;  // src-size 0: nothing is read, destination zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void CpAsync16(void* smemDst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smemDst));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void CpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int kRowBlock = 8;  // assignment rows held in registers per block of the rolling prefetch window
+
+// K: codewords per subspace; CPT: channels per thread; TN: images per CTA; PFL: subspaces per LUT chunk;
 // PRE: assignments stored as byte offsets (idx*4)
-template <int K, int CPT, int TN, int PF, bool PRE>
+//
+// Per chunk of PFL subspaces:  (1) the chunk's input slice and codebook rows were copied into shared memory by
+// cp.async while the PREVIOUS chunk was being gathered; (2) the LUT slice [TN][PFL][K] is built from them
+// (shared -> shared, no global latency); (3) the chunk's assignment rows stream through a rolling register window
+// (block r+1 is in flight while block r is consumed) and are gathered against the LUT slice.
+template <int K, int CPT, int TN, int PFL, bool PRE>
 __global__ void __launch_bounds__(kFcThreads, 2) fc_aprx_kernel(const FcArgs a) {
-  extern __shared__ __align__(16) float lut[];  // [TN][PF][K]
+  extern __shared__ __align__(16) unsigned char smraw[];
   using AV = typename AsmtVec<CPT>::type;
+  constexpr int U = kRowBlock;
+  static_assert(PFL % U == 0, "chunk must be a whole number of row blocks");
+  const int d = a.d;
+  const int xlen = TN * PFL * d;            // staged input slice of one chunk (floats)
+  const int xpad = (xlen + 3) & ~3;
+  const int clen = PFL * K * d;             // staged codebook rows of one chunk (floats, multiple of 4)
+  float* lut = reinterpret_cast<float*>(smraw);  // [TN][PFL][K]
+  float* xN = lut + TN * PFL * K;                 // [2][xpad]
+  float* cN = xN + 2 * xpad;                      // [2][clen]
+
   const int tid = threadIdx.x;
   const int o0 = (blockIdx.x * kFcThreads + tid) * CPT;
   const int n0 = blockIdx.y * TN;
@@ -65,90 +97,107 @@ __global__ void __launch_bounds__(kFcThreads, 2) fc_aprx_kernel(const FcArgs a) 
   const int s_end = min(a.S, s_begin + a.s_per_split);
   const bool live = o0 < a.DoutPad;
 
+  // asynchronous staging of chunk `sc` into buffer `buf`
+  auto fetch = [&](int sc, int buf) {
+    float* xb = xN + buf * xpad;
+    float* cb = cN + buf * clen;
+    const int per = PFL * d;
+    for (int e = tid; e < xlen; e += kFcThreads) {
+      const int nl = e / per, i = e - nl * per;
+      const int f = sc * d + i;
+      const int n = n0 + nl;
+      const bool ok = n < a.N && f < a.Din && (sc + i / d) < s_end;
+      int off = 0;
+      if (ok) off = a.srcoff ? __ldg(a.srcoff + f) : f;  // NHWC source read in NCHW-flatten order
+      CpAsync4(xb + e, a.src + (ok ? static_cast<size_t>(n) * a.Din + off : 0), ok);
+    }
+    const float* cg = a.ctrd + static_cast<size_t>(sc) * K * d;
+    for (int v = tid; v < clen / 4; v += kFcThreads) {
+      const bool ok = (sc + (4 * v) / (K * d)) < s_end;
+      CpAsync16(cb + 4 * v, cg + (ok ? 4 * v : 0), ok);
+    }
+    CpAsyncCommit();
+  };
+
   float acc[TN][CPT];
 #pragma unroll
   for (int c = 0; c < CPT; c++) {
-    const float b = (split == 0 && o0 + c < a.Dout) ? __ldg(a.bias + o0 + c) : 0.0f;
+    const float bv = (split == 0 && o0 + c < a.Dout) ? __ldg(a.bias + o0 + c) : 0.0f;
 #pragma unroll
-    for (int nl = 0; nl < TN; nl++) acc[nl][c] = b;
+    for (int nl = 0; nl < TN; nl++) acc[nl][c] = bv;
   }
 
-  for (int sc = s_begin; sc < s_end; sc += PF) {
-    // (1) start the assignment stream for this chunk
-    AV areg[PF];
+  if (s_begin < s_end) fetch(s_begin, 0);
+  int buf = 0;
+  for (int sc = s_begin; sc < s_end; sc += PFL, buf ^= 1) {
+    // (0) first block of assignment rows: in flight during the LUT build
+    AV win[U];
 #pragma unroll
-    for (int r = 0; r < PF; r++) {
+    for (int r = 0; r < U; r++) {
       const int s = sc + r;
-      if (live && s < s_end) {
-        areg[r] = LoadStream(reinterpret_cast<const AV*>(a.asmt + static_cast<size_t>(s) * a.DoutPad + o0));
-      } else {
-        Zero(areg[r]);
-      }
+      if (live && s < s_end) win[r] = LoadStream(reinterpret_cast<const AV*>(a.asmt + static_cast<size_t>(s) * a.DoutPad + o0));
+      else Zero(win[r]);
     }
-    // (2) build the LUT slice of this chunk.  A thread owns (subspace r, codeword k) pairs: it loads the pair's
-    //     codebook row and source offsets once and sweeps the TN images (x loads are warp-broadcast).
-    __syncthreads();  // the previous chunk's gather is done with `lut`
-    for (int pr = tid; pr < PF * K; pr += kFcThreads) {
-      const int k = pr % K;
-      const int r = pr / K;
-      const int s = sc + r;
-      const int f0 = s * a.d;
-      const int sel = (s < s_end) ? min(a.Din - f0, a.d) : 0;
-      const float* crow = a.ctrd + (static_cast<size_t>(s) * K + k) * a.d;
-      if (a.d <= 8) {
-        float c[8];
-        int off[8];
+    // (1) staged operands of this chunk have landed; the previous gather is done with `lut`
+    CpAsyncWaitAll();
+    __syncthreads();
+    // (2) LUT slice: thread owns (subspace r, codeword k) pairs and sweeps the TN images
+    {
+      const float* xb = xN + buf * xpad;
+      const float* cb = cN + buf * clen;
+      for (int pr = tid; pr < PFL * K; pr += kFcThreads) {
+        const int r = pr / K, k = pr % K;
+        const float* c = cb + static_cast<size_t>(pr) * d;
+        if (d == 4) {
+          const float4 cv = *reinterpret_cast<const float4*>(c);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          c[j] = 0.0f;
-          off[j] = 0;
-          if (j < sel) {
-            const int f = f0 + j;
-            off[j] = a.hw ? ((f % a.hw) * a.ch + f / a.hw) : f;  // NHWC source read in NCHW-flatten order
-            c[j] = __ldg(crow + j);
+          for (int nl = 0; nl < TN; nl++) {
+            const float4 xv = *reinterpret_cast<const float4*>(xb + nl * PFL * 4 + r * 4);
+            float v = __fmul_rn(xv.x, cv.x);           // 0 + x0*c0 == x0*c0 exactly
+            v = __fadd_rn(v, __fmul_rn(xv.y, cv.y));
+            v = __fadd_rn(v, __fmul_rn(xv.z, cv.z));
+            v = __fadd_rn(v, __fmul_rn(xv.w, cv.w));
+            lut[(nl * PFL + r) * K + k] = v;
           }
-        }
+        } else {
 #pragma unroll
-        for (int nl = 0; nl < TN; nl++) {
-          const int n = n0 + nl;
-          float v = 0.0f;
-          if (n < a.N) {
-            const float* x = a.src + static_cast<size_t>(n) * a.Din;
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-              if (j < sel) v = __fadd_rn(v, __fmul_rn(__ldg(x + off[j]), c[j]));
+          for (int nl = 0; nl < TN; nl++) {
+            const float* x = xb + nl * PFL * d + r * d;
+            float v = 0.0f;
+            for (int j = 0; j < d; j++) v = __fadd_rn(v, __fmul_rn(x[j], c[j]));
+            lut[(nl * PFL + r) * K + k] = v;
           }
-          lut[(nl * PF + r) * K + k] = v;
-        }
-      } else {
-        for (int nl = 0; nl < TN; nl++) {
-          const int n = n0 + nl;
-          float v = 0.0f;
-          if (n < a.N) {
-            const float* x = a.src + static_cast<size_t>(n) * a.Din;
-            for (int j = 0; j < sel; j++) {
-              const int f = f0 + j;
-              const int off = a.hw ? ((f % a.hw) * a.ch + f / a.hw) : f;
-              v = __fadd_rn(v, __fmul_rn(__ldg(x + off), __ldg(crow + j)));
-            }
-          }
-          lut[(nl * PF + r) * K + k] = v;
         }
       }
     }
     __syncthreads();
-    // (3) gather-accumulate.  Rows past s_end hold zeros and index 0, so no tail guard is needed.
+    // (3) next chunk's operands fly in while this one is gathered
+    if (sc + PFL < s_end) fetch(sc + PFL, buf ^ 1);
     const char* lutb = reinterpret_cast<const char*>(lut);
 #pragma unroll
-    for (int r = 0; r < PF; r++) {
+    for (int rb = 0; rb < PFL; rb += U) {
+      AV cur[U];
 #pragma unroll
-      for (int c = 0; c < CPT; c++) {
-        const uint32_t w = Word(areg[r], c >> 2);
-        uint32_t off = (w >> (8 * (c & 3))) & 0xFFu;
-        if (!PRE) off <<= 2;
+      for (int r = 0; r < U; r++) cur[r] = win[r];
+      if (rb + U < PFL) {
 #pragma unroll
-        for (int nl = 0; nl < TN; nl++) {
-          acc[nl][c] += *reinterpret_cast<const float*>(lutb + (nl * PF + r) * K * 4 + off);
+        for (int r = 0; r < U; r++) {
+          const int s = sc + rb + U + r;
+          if (live && s < s_end) win[r] = LoadStream(reinterpret_cast<const AV*>(a.asmt + static_cast<size_t>(s) * a.DoutPad + o0));
+          else Zero(win[r]);
+        }
+      }
+      // rows past s_end hold index 0 and their LUT rows are zero, so no tail guard is needed
+#pragma unroll
+      for (int r = 0; r < U; r++) {
+#pragma unroll
+        for (int c = 0; c < CPT; c++) {
+          const uint32_t w = Word(cur[r], c >> 2);
+          uint32_t off = (w >> (8 * (c & 3))) & 0xFFu;
+          if (!PRE) off <<= 2;
+#pragma unroll
+          for (int nl = 0; nl < TN; nl++)
+            acc[nl][c] += *reinterpret_cast<const float*>(lutb + (nl * PFL + rb + r) * K * 4 + off);
         }
       }
     }
@@ -186,7 +235,12 @@ __global__ void fc_reduce_kernel(const float* __restrict__ partial, float* __res
 
 template <int K, int CPT, int TN, int PF, bool PRE>
 int Launch(const FcArgs& a, dim3 grid, cudaStream_t st) {
-  const size_t smem = sizeof(float) * TN * PF * K;
+  const size_t xpad = (static_cast<size_t>(TN) * PF * a.d + 3) & ~static_cast<size_t>(3);
+  const size_t smem = sizeof(float) * (static_cast<size_t>(TN) * PF * K + 2 * xpad + 2 * static_cast<size_t>(PF) * K * a.d);
+  if (smem > 200 * 1024) {
+    qcnn::SetError("qcnn_fc_aprx_forward: K=%d d=%d needs %zu bytes of shared memory per CTA", K, a.d, smem);
+    return 1;
+  }
   auto kern = fc_aprx_kernel<K, CPT, TN, PF, PRE>;
   if (smem > 48 * 1024) QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kFcThreads, smem, st>>>(a);
@@ -197,9 +251,9 @@ int Launch(const FcArgs& a, dim3 grid, cudaStream_t st) {
 template <int K, bool PRE>
 int LaunchK(const FcArgs& a, int tn, dim3 grid, cudaStream_t st) {
   switch (tn) {
-    case 1: return Launch<K, 16, 1, 16, PRE>(a, grid, st);
-    case 4: return Launch<K, 8, 4, (K <= 64 ? 16 : 8), PRE>(a, grid, st);
-    default: return Launch<K, 8, 8, 8, PRE>(a, grid, st);
+    case 1: return Launch<K, 16, 1, (K <= 64 ? 16 : 8), PRE>(a, grid, st);
+    case 4: return Launch<K, 8, 4, (K <= 32 ? 32 : (K <= 64 ? 16 : 8)), PRE>(a, grid, st);
+    default: return Launch<K, 8, 8, (K <= 32 ? 32 : (K <= 64 ? 16 : 8)), PRE>(a, grid, st);
   }
 }
 
@@ -209,9 +263,8 @@ namespace qcnn {
 
 // chunk length (subspaces) of the instantiation chosen for (K, tn) -- must mirror LaunchK above
 static int ChunkLen(int K, int tn) {
-  if (tn == 1) return 16;
-  if (tn == 4) return K <= 64 ? 16 : 8;
-  return 8;
+  if (tn == 1) return K <= 64 ? 16 : 8;
+  return K <= 32 ? 32 : (K <= 64 ? 16 : 8);
 }
 
 int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st) {
@@ -222,7 +275,7 @@ int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaS
   a.src = src; a.dst = dst; a.partial = nullptr;
   a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
   a.N = N; a.Din = L->Din; a.Dout = L->Dout; a.DoutPad = L->DoutPad; a.S = L->S; a.K = L->K; a.d = L->d;
-  a.hw = L->src_h * L->src_w; a.ch = L->src_c;
+  a.srcoff = L->d_srcoff;
   a.relu = relu;
 
   // batch tile: 1 (latency path, 16 channels/thread, 128-bit loads), 4 or 8 images per CTA

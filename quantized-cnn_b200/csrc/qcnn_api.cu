@@ -206,10 +206,17 @@ int qcnn_fc_layer_create(qcnn_ctx* ctx, int Din, int Dout, int S, int K, int d, 
 
 int qcnn_fc_layer_set_src_nhwc(qcnn_layer* L, int H, int W, int C) {
   QCNN_CHECK(L && L->kind == QCNN_KIND_FC, "qcnn_fc_layer_set_src_nhwc: not an FC layer");
+  if (L->d_srcoff) { cudaFree(L->d_srcoff); L->d_srcoff = nullptr; }
   if (H == 0 && W == 0 && C == 0) { L->src_h = L->src_w = L->src_c = 0; return 0; }
   QCNN_CHECK(H >= 1 && W >= 1 && C >= 1 && H * W * C == L->Din, "qcnn_fc_layer_set_src_nhwc: H*W*C=%d != Din=%d",
              H * W * C, L->Din);
   L->src_h = H; L->src_w = W; L->src_c = C;
+  // flattened NCHW feature f = c*H*W + hw  ->  NHWC element offset hw*C + c
+  std::vector<int> off(L->Din);
+  const int hw = H * W;
+  for (int f = 0; f < L->Din; f++) off[f] = (f % hw) * C + f / hw;
+  QCNN_CUDA(cudaMalloc(&L->d_srcoff, sizeof(int) * L->Din));
+  QCNN_CUDA(cudaMemcpy(L->d_srcoff, off.data(), sizeof(int) * L->Din, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -241,6 +248,7 @@ void qcnn_layer_destroy(qcnn_layer* L) {
   if (L->d_ctrd) cudaFree(L->d_ctrd);
   if (L->d_bias) cudaFree(L->d_bias);
   if (L->d_partial) cudaFree(L->d_partial);
+  if (L->d_srcoff) cudaFree(L->d_srcoff);
   delete L;
 }
 

@@ -54,7 +54,7 @@ struct FcArgs {
   const uint8_t* asmt; // [S][DoutPad], value = idx << kshift
   const float* bias;
   int N, Din, Dout, DoutPad, S, K, d;
-  int hw, ch;          // source is NHWC [hw][ch] per image (hw == 0: flat)
+  const int* srcoff;   // [Din] element offset of flattened feature f inside one source image (NULL: identity)
   int s_per_split, nsplit;
   int relu;
 };
@@ -95,6 +95,7 @@ struct qcnn_layer {
   int Din, Dout, DoutPad;
   // FC source permutation (NHWC map) / conv NCHW source
   int src_h, src_w, src_c;
+  int* d_srcoff;        // FC: NCHW-flatten index -> NHWC element offset (NULL when the source is flat)
   int src_nchw;
   // device parameters
   float* d_ctrd;

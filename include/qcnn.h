@@ -95,6 +95,11 @@ QCNN_API int qcnn_conv_aprx_forward(qcnn_layer* layer, const float* src, int N, 
 QCNN_API int qcnn_fc_aprx_forward(qcnn_layer* layer, const float* src, int N, float* dst, int fuse_relu,
                                   void* stream);
 
+/* same, but src is always the flat [N][Din] vector in the reference's (NCHW-flatten) feature order, even for a layer
+ * whose NHWC fold (qcnn_fc_layer_set_src_nhwc) is enabled -- what CaffeEva::CalcFeatMap_FCntAprx itself receives */
+QCNN_API int qcnn_fc_aprx_forward_flat(qcnn_layer* layer, const float* src, int N, float* dst, int fuse_relu,
+                                       void* stream);
+
 /* ---- supporting layers (src/CaffeEva.cc:1027-1116, 870-921) ---------------------------------------------- */
 QCNN_API int qcnn_relu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, void* stream);
 QCNN_API int qcnn_lrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha,

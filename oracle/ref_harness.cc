@@ -30,6 +30,7 @@
 #define private public
 #include "include/CaffeEva.h"
 #include "include/FileIO.h"
+#include "include/CaffeEvaWrapper.h"
 #undef private
 
 namespace {
@@ -288,6 +289,37 @@ int ref_write_bin_f32(const char* path, int dimCnt, const int* dims, const float
   Matrix<float> m(dimCnt, dims);
   memcpy(m.GetDataPtr(), data, sizeof(float) * m.GetEleCnt());
   return FileIO::WriteBinFile(path, m) ? 0 : -1;
+}
+
+// CaffeEvaWrapper::SetPath + SetModel(AlexNet, Aprx) (CaffeEvaWrapper.cc:15-151); returns a handle or NULL
+void* ref_wrapper_create(const char* mainDir, const char* clsNames, const char* imgLabels) {
+  StdoutMute mute(true);
+  CaffeEvaWrapper* w = new CaffeEvaWrapper();
+  if (!w->SetPath(mainDir, clsNames, imgLabels ? imgLabels : "")) return nullptr;
+  if (!w->SetModel(ENUM_CaffeModel::AlexNet, ENUM_CompMethod::Aprx)) return nullptr;
+  return w;
+}
+
+// CaffeEvaWrapper::Proc (CaffeEvaWrapper.cc:153-209): top-k indices / probabilities of one BMP
+int ref_wrapper_proc(void* h, const char* bmpPath, int k, int* idx, float* prob) {
+  StdoutMute mute(true);
+  CaffeEvaWrapper* w = static_cast<CaffeEvaWrapper*>(h);
+  CaffeEvaRslt r;
+  r.clsCntPred = k;
+  if (!w->Proc(bmpPath, &r)) return -1;
+  for (int i = 0; i < k; i++) { idx[i] = r.clsIdxLst[i]; prob[i] = r.clsProbLst[i]; }
+  return 0;
+}
+
+// BmpImgIO::Load (BmpImgIO.cc:40-71) with the wrapper's AlexNet recipe: out [3][227][227] BGR, mean-subtracted
+int ref_wrapper_load_bmp(void* h, const char* bmpPath, float* out, int cap) {
+  StdoutMute mute(true);
+  CaffeEvaWrapper* w = static_cast<CaffeEvaWrapper*>(h);
+  Matrix<float> img;
+  if (!w->bmpImgIOObj.Load(bmpPath, &img)) return -1;
+  int n = img.GetEleCnt();
+  memcpy(out, img.GetDataPtr(), sizeof(float) * std::min(n, cap));
+  return n;
 }
 
 }  // extern "C"

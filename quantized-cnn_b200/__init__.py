@@ -75,6 +75,7 @@ _SIGS = {
     "qcnn_layer_read_asmt_h": (_i, [_vp, _vp, _sz]),
     "qcnn_conv_aprx_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "qcnn_fc_aprx_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "qcnn_fc_aprx_forward_flat": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "qcnn_relu": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "qcnn_lrn": (_i, [_vp, _vp, _vp, _sz, _i, _i, _f, _f, _f, _vp]),
     "qcnn_maxpool": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -330,6 +330,15 @@ int qcnn_fc_aprx_forward(qcnn_layer* L, const float* src, int N, float* dst, int
   return LaunchFc(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
 }
 
+int qcnn_fc_aprx_forward_flat(qcnn_layer* L, const float* src, int N, float* dst, int fuse_relu, void* stream) {
+  QCNN_CHECK(L && src && dst, "qcnn_fc_aprx_forward_flat: NULL argument");
+  int* saved = L->d_srcoff;
+  L->d_srcoff = nullptr;
+  const int rc = LaunchFc(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
+  L->d_srcoff = saved;
+  return rc;
+}
+
 int qcnn_relu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, void* stream) {
   QCNN_CHECK(ctx && src && dst, "qcnn_relu: NULL argument");
   return LaunchRelu(ctx, src, dst, n, static_cast<cudaStream_t>(stream));

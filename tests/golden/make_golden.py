@@ -9,6 +9,7 @@ Outputs (all small):
                     top-5, per-layer (sum, l2, max) checksums of featMapLst
   synth_layers.npz  reference CalcFeatMap outputs of small synthetic conv / FC / LRN / pool / softmax layers
                     (inputs + parameters stored alongside)
+  bmp_top5.npz      top-5 of CaffeEvaWrapper::Proc on the ten shipped BMPs + fingerprints of BmpImgIO::Load outputs
   cbn_vectors.npz   byte images of .cbn / .bin files written by the reference's own FileIO for 4/5/7/8-bit tables
 """
 import os
@@ -112,11 +113,37 @@ def cbn_vectors():
     np.savez_compressed(os.path.join(OUT, "cbn_vectors.npz"), **out)
 
 
+def bmp_top5():
+    """CaffeEvaWrapper::Proc (reference src/CaffeEvaWrapper.cc:153-209) on the ten shipped BMPs + a fingerprint of
+    BmpImgIO::Load's output tensor for each."""
+    import ctypes as C
+    R = po.ref()
+    R.ref_wrapper_create.restype = C.c_void_p
+    d = po.REF_DATA
+    h = C.c_void_p(R.ref_wrapper_create(d.encode(), (d + "/Cls.Names/class_names.txt").encode(),
+                                        (d + "/Cls.Names/image_labels.txt").encode()))
+    out = {}
+    for i in range(1, 11):
+        bmp = ("%s/Bmp.Files/ILSVRC2012_val_%08d.BMP" % (d, i)).encode()
+        idx = np.zeros(5, np.int32)
+        pr = np.zeros(5, np.float32)
+        assert R.ref_wrapper_proc(h, bmp, 5, idx.ctypes.data_as(C.c_void_p), pr.ctypes.data_as(C.c_void_p)) == 0
+        img = np.zeros(3 * 227 * 227, np.float32)
+        assert R.ref_wrapper_load_bmp(h, bmp, img.ctypes.data_as(C.c_void_p), img.size) == img.size
+        a = img.astype(np.float64)
+        out["top5_idx_%02d" % i] = idx
+        out["top5_prob_%02d" % i] = pr
+        out["img_cks_%02d" % i] = np.array([a.sum(), np.sqrt((a * a).sum()), a.max(), a.min()])
+        out["img_head_%02d" % i] = img[:64].copy()
+    np.savez_compressed(os.path.join(OUT, "bmp_top5.npz"), **out)
+
+
 if __name__ == "__main__":
     assert po.have_ref(), "build oracle/_ref first (make -C oracle ref data)"
     po.build()
     alexnet_kat()
     synth_layers()
     cbn_vectors()
+    bmp_top5()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

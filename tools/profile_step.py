@@ -26,6 +26,10 @@ def main():
     net = q.Net(ctx, d, pfx, "AlexNet")
     img = torch.from_numpy(bench.lcg_images(args.batch, 12345)).cuda()
     prob = torch.empty((args.batch, 1000), dtype=torch.float32, device="cuda")
+    for l in range(net.layer_count):
+        pl = net.pq_layer(l)
+        if pl is not None:
+            print("layer", l, pl.describe(args.batch))
     for _ in range(args.iters):
         net.forward(img, prob=prob)
     torch.cuda.synchronize()

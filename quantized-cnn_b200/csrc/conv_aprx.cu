@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -352,6 +353,255 @@ __global__ void __launch_bounds__(MAXT, 1) conv_s1_kernel(const ConvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// stride-1 kernel, tensor-core LUT stage (K = 128 codewords, subspaces of <= 8 dims)
+//
+// The LUT of a subspace is the dense contraction  LUT[k][p] = sum_j ctrd[s][k][j] * x[p][j]  = C (128 x 8) * X^T (8 x N).
+// Here it runs on the 5th-generation tensor cores: ONE thread issues three tcgen05.mma kind::tf32 (M = 128, N <= 256,
+// K = 8) per subspace -- the 3xTF32 split  C_hi*X_hi + C_hi*X_lo + C_lo*X_hi  keeps fp32-level accuracy (measured
+// 7e-7 of the LUT magnitude, tools/tc_lut_test.cu) -- with the accumulator in TMEM (lane = codeword, column =
+// position).  The MMA of subspace s+1 executes asynchronously WHILE the CUDA cores gather subspace s out of shared
+// memory; at the stage boundary the finished accumulator is drained TMEM -> registers -> lut[k][p] (tcgen05.ld +
+// 128-bit stores, bank-conflict free because the row pitch is 4 mod 32 words).  Operands reach the canonical K-major
+// no-swizzle UMMA tiles through cp.async (raw) + a hi/lo split pass.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t SmemU32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// canonical K-major / SWIZZLE_NONE operand tile (tf32): rows in groups of 8, per group K-chunk 0 (8 rows x 16 B) then
+// K-chunk 1; element (row r, k) -> float index below.  Descriptor: LBO = 128 B (K chunks), SBO = 256 B (row groups).
+__device__ __forceinline__ int UmmaIdx(int r, int k) { return (r >> 3) * 64 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3); }
+__device__ __forceinline__ uint64_t UmmaDesc(const void* smem) {
+  uint64_t d = (static_cast<uint64_t>(SmemU32(smem)) >> 4) & 0x3FFF;
+  d |= static_cast<uint64_t>(8) << 16;    // leading byte offset 128 B >> 4
+  d |= static_cast<uint64_t>(16) << 32;   // stride byte offset 256 B >> 4
+  d |= static_cast<uint64_t>(1) << 46;    // descriptor version: Blackwell
+  return d;
+}
+__device__ __forceinline__ void UmmaTf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmemD), "l"(descA), "l"(descB),
+               "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void MbarWait(uint64_t* mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(SmemU32(mbar)), "r"(parity) : "memory");
+  }
+}
+// hi = value truncated to tf32 (what the tensor core reads), lo = exact remainder
+__device__ __forceinline__ void SplitTf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = v - hi;
+}
+
+struct SmemLayoutTc {
+  float* lut;       // [128][PP]
+  uint32_t* idx;    // [taps][CT]
+  float* aHi;       // [128 x 8] canonical
+  float* aLo;
+  float* bHi;       // [NM x 8] canonical
+  float* bLo;
+  float* xr;        // [NM][8] raw pixels of the next subspace (cp.async target)
+  float* cr;        // [128][8] raw codebook of the next subspace
+  uint8_t* idN;     // [taps*CT] raw assignment slice
+  int* posoff;      // [NM]
+  uint64_t* mbar;
+  uint32_t* tmemBase;
+};
+__device__ __forceinline__ SmemLayoutTc CarveTc(unsigned char* smem, int PP, int NM, int taps, int CT) {
+  SmemLayoutTc s;
+  s.lut = reinterpret_cast<float*>(smem);
+  s.idx = reinterpret_cast<uint32_t*>(s.lut + 128 * PP);
+  s.aHi = reinterpret_cast<float*>(s.idx + taps * CT);
+  s.aLo = s.aHi + 1024;
+  s.bHi = s.aLo + 1024;
+  s.bLo = s.bHi + NM * 8;
+  s.xr = s.bLo + NM * 8;
+  s.cr = s.xr + NM * 8;
+  s.posoff = reinterpret_cast<int*>(s.cr + 1024);
+  s.mbar = reinterpret_cast<uint64_t*>(s.posoff + NM);
+  s.tmemBase = reinterpret_cast<uint32_t*>(s.mbar + 1);
+  s.idN = reinterpret_cast<uint8_t*>(s.tmemBase + 2);
+  return s;
+}
+
+template <int CPT, int J, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) conv_s1_tc_kernel(const ConvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int taps = a.ksz * a.ksz;
+  const int NM = a.RI;  // MMA N: LUT columns produced per subspace (multiple of 32, <= 256); a.RI is reused for it
+  const SmemLayoutTc sm = CarveTc(smem, a.PP, NM, taps, a.CT);
+
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+  const int pw = warp % a.pwarps, cw = warp / a.pwarps;
+  int b = blockIdx.x;
+  const int strip = b % a.nstrips; b /= a.nstrips;
+  const int ct = b % a.nct;
+  const int g = b / a.nct;
+  const int n = blockIdx.y;
+  const int r0 = strip * a.R;
+  const int hin0 = r0 - a.pad;
+  const int rowsIn = a.R + a.ksz - 1;
+  const int q0 = pw * 32 * J + lane;
+  const int cbase = ct * a.CT + cw * CPT;
+  const float* src = a.src + static_cast<size_t>(n) * a.Hi * a.Wi * a.Cin + g * a.Cg;
+  const uint8_t* asmtG = a.asmt + static_cast<size_t>(g) * a.S * taps * a.KgPad + ct * a.CT;
+
+  for (int pos = tid; pos < NM; pos += T) {
+    int off = -1;
+    const int pp = pos - a.pad;
+    if (pp >= 0) {
+      const int ri = pp / a.PW, wi = pp - ri * a.PW;
+      const int hi = hin0 + ri;
+      if (ri < rowsIn && wi < a.Wi && hi >= 0 && hi < a.Hi) off = (hi * a.Wi + wi) * a.Cin;
+    }
+    sm.posoff[pos] = off;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(sm.tmemBase)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemU32(sm.mbar)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  Acc<CPT, J> acc;
+  {
+    float bv[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; c++) bv[c] = __ldg(a.bias + g * a.Kg + cbase + c);
+    acc.Fill(bv);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();  // posoff, mbarrier, TMEM base visible
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmemD = *sm.tmemBase;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NM >> 3) << 17) | (8u << 24);
+  const uint32_t rowBytes = static_cast<uint32_t>(a.PP) * 4u;
+
+  // raw operands of subspace s: pixels [NM][8] and codebook [128][8], zero beyond the subspace's real dims
+  auto fetchRaw = [&](int s) {
+    const int nj = max(0, min(8, min(a.Cg - s * a.d, a.d)));
+    const float* cg = a.ctrd + static_cast<size_t>(s) * 128 * a.d;
+    for (int e = tid; e < 1024; e += T) {
+      const int k = e >> 3, jj = e & 7;
+      CpAsync4(sm.cr + e, cg + (jj < nj ? k * a.d + jj : 0), jj < nj);
+    }
+    const int ch0 = s * a.d;
+    for (int e = tid; e < NM * 8; e += T) {
+      const int pos = e >> 3, jj = e & 7;
+      const int off = sm.posoff[pos];
+      const bool ok = off >= 0 && jj < nj;
+      CpAsync4(sm.xr + e, src + (ok ? off + ch0 + jj : 0), ok);
+    }
+  };
+  // raw -> hi/lo canonical UMMA tiles (generic-proxy writes, published to the async proxy by the caller's fence)
+  auto splitOperands = [&]() {
+    for (int e = tid; e < 1024; e += T) {
+      float hi, lo;
+      SplitTf32(sm.cr[e], hi, lo);
+      const int i = UmmaIdx(e >> 3, e & 7);
+      sm.aHi[i] = hi;
+      sm.aLo[i] = lo;
+    }
+    for (int e = tid; e < NM * 8; e += T) {
+      float hi, lo;
+      SplitTf32(sm.xr[e], hi, lo);
+      const int i = UmmaIdx(e >> 3, e & 7);
+      sm.bHi[i] = hi;
+      sm.bLo[i] = lo;
+    }
+  };
+  auto issueMma = [&]() {  // one thread: D = Ah*Bh + Ah*Bl + Al*Bh, then signal the mbarrier when all three retire
+    const uint64_t dAh = UmmaDesc(sm.aHi), dAl = UmmaDesc(sm.aLo), dBh = UmmaDesc(sm.bHi), dBl = UmmaDesc(sm.bLo);
+    UmmaTf32(tmemD, dAh, dBh, idesc, 0);
+    UmmaTf32(tmemD, dAh, dBl, idesc, 1);
+    UmmaTf32(tmemD, dAl, dBh, idesc, 1);
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemU32(sm.mbar)) : "memory");
+  };
+
+  // prologue: LUT(0) on the tensor core, operands of subspace 1 + assignment slice 0 in flight
+  fetchRaw(0);
+  CpAsyncCommit();
+  CpAsyncWaitAll();
+  __syncthreads();
+  splitOperands();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) issueMma();
+  if (a.S > 1) fetchRaw(1);
+  FetchOffsets(sm.idN, asmtG, taps, a.CT, a.KgPad, tid, T);
+  CpAsyncCommit();
+
+  for (int s = 0; s < a.S; s++) {
+    MbarWait(sm.mbar, s & 1);   // LUT(s) is complete in TMEM; the operand tiles are free again
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    CpAsyncWaitAll();
+    __syncthreads();            // (A) gather(s-1) is done with lut/idx; raw operands of s+1 and idN(s) are visible
+    // drain TMEM -> lut: warp w owns TMEM lanes [32 (w%4), +32) = codewords; 32 columns (positions) per load
+    {
+      const int q = warp & 3;
+      const int k = q * 32 + lane;
+      float* row = sm.lut + k * a.PP;
+      for (int c = warp >> 2; c < (NM >> 5); c += (nwarps + 3 - q) >> 2) {
+        uint32_t r[32];
+        const uint32_t taddr = tmemD + (static_cast<uint32_t>(q * 32) << 16) + c * 32;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                     "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+                       "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+                       "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+                       "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(row + c * 32 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+      }
+    }
+    CommitOffsets(sm.idN, sm.idx, taps, a.CT, rowBytes, tid, T);
+    if (s + 1 < a.S) splitOperands();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();            // (B) lut + idx ready, TMEM drained, operand tiles of s+1 published
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (s + 1 < a.S) {
+      if (tid == 0) issueMma();                  // LUT(s+1) is computed while subspace s is gathered
+      if (s + 2 < a.S) fetchRaw(s + 2);
+      FetchOffsets(sm.idN, asmtG + static_cast<size_t>(s + 1) * taps * a.KgPad, taps, a.CT, a.KgPad, tid, T);
+      CpAsyncCommit();
+    }
+    // ---- gather stage ----
+    const char* lutq = reinterpret_cast<const char*>(sm.lut) + q0 * 4;
+    const uint32_t* ip = sm.idx + cw * CPT;
+    for (int kh = 0; kh < a.ksz; kh++) {
+      for (int kw = 0; kw < a.ksz; kw++) {
+        GatherTap<CPT, J>(acc, lutq + (kh * a.PW + kw) * 4, ip);
+        ip += a.CT;
+      }
+    }
+  }
+
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int q = q0 + 32 * j;
+    const int r = q / a.PW, wo = q - r * a.PW;
+    const int ho = r0 + r;
+    if (r < a.R && wo < a.Wo && ho < a.Ho) {
+      float* out = a.dst + ((static_cast<size_t>(n) * a.Ho + ho) * a.Wo + wo) * a.Cout + g * a.Kg + cbase;
+      StoreChannels<CPT, J>(out, acc, j, a.relu);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "r"(256) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // rolling-row kernel (any stride)
 // ------------------------------------------------------------------------------------------------------------
 template <int CPT, int J, int MAXT>
@@ -489,6 +739,10 @@ int LaunchBound(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
     auto kern = conv_s1_kernel<CPT, J, MAXT>;
     QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     kern<<<grid, p.threads, p.smem, st>>>(a);
+  } else if (p.kernel == 2) {
+    auto kern = conv_s1_tc_kernel<CPT, J, MAXT>;
+    QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    kern<<<grid, p.threads, p.smem, st>>>(a);
   } else {
     auto kern = conv_roll_kernel<CPT, J, MAXT>;
     QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
@@ -528,6 +782,8 @@ int PlanConv(qcnn_layer* L, int N) {
   double dimsSum = 0;  // sum over subspaces of the dims that exist
   for (int s = 0; s < L->S; s++) dimsSum += std::max(0, std::min(Cg - s * L->d, L->d));
   const double ipe = 0.66 * (dimsSum / L->S) + 0.3;  // issue slots per LUT entry
+  // tensor-core LUT stage: 128 codewords (MMA M), every subspace <= 8 dims (one K = 8 tf32 step); env QCNN_NO_TC=1 disables
+  const bool tcOk = L->stride == 1 && L->K == 128 && L->d <= 8 && getenv("QCNN_NO_TC") == nullptr;
   const int cpts[2] = {32, 16};
   for (int ci = 0; ci < 2; ci++) {
     const int CPT = cpts[ci];
@@ -539,62 +795,76 @@ int PlanConv(qcnn_layer* L, int N) {
         if (CT % CPT != 0 || CT % 16 != 0) continue;
         const int cwarps = CT / CPT;
         for (int R = 1; R <= L->Ho; R++) {
-          ConvPlan p;
-          memset(&p, 0, sizeof(p));
-          ConvArgs& a = p.a;
-          a.R = R;
-          a.nstrips = CeilDiv(L->Ho, R);
-          a.CT = CT; a.nct = nct; a.cwarps = cwarps;
-          a.ksplit = 1;
-          double gatherSlots, builtEntries, phases;
-          int warps;
-          if (L->stride == 1) {
-            p.kernel = 0;
-            a.PW = L->Win + L->pad;
-            a.RI = R + L->ksz - 1;
-            a.pwarps = CeilDiv(R * a.PW, 32 * J);
-            a.rgroups = 1;
-            const int need1 = a.RI * a.PW + std::max(L->pad, L->ksz - 1) + 1;
-            const int need2 = a.pwarps * 32 * J + (L->ksz - 1) * a.PW + (L->ksz - 1) + 1;
-            a.PP = RoundUp(std::max(need1, need2), 4);
-            warps = a.pwarps * cwarps;
-            gatherSlots = static_cast<double>(a.pwarps) * J * taps * L->S * CT;   // wavefronts of LUT reads
-            builtEntries = static_cast<double>(a.PP) * L->K * L->S;
-            phases = L->S;
-          } else {
-            p.kernel = 1;
-            a.rgroups = CeilDiv(L->ksz, L->stride);
-            a.pwarps = CeilDiv(L->Wo, 32 * J);
-            const int ph1 = CeilDiv(L->Win + 2 * L->pad, L->stride);
-            const int ph2 = a.pwarps * 32 * J + (L->ksz - 1) / L->stride + 1;
-            a.PW = std::max(ph1, ph2);           // phase length
-            a.PP = RoundUp(a.PW * L->stride, 4);
-            a.RI = 0;
-            warps = a.pwarps * cwarps * a.rgroups;
-            const double rowsIn = (R - 1) * L->stride + L->ksz;
-            gatherSlots = static_cast<double>(a.pwarps) * J * R * taps * L->S * CT;
-            builtEntries = static_cast<double>(a.PP) * L->K * L->S * rowsIn;
-            phases = L->S * rowsIn;
+          for (int tc = 0; tc <= (tcOk ? 1 : 0); tc++) {
+            ConvPlan p;
+            memset(&p, 0, sizeof(p));
+            ConvArgs& a = p.a;
+            a.R = R;
+            a.nstrips = CeilDiv(L->Ho, R);
+            a.CT = CT; a.nct = nct; a.cwarps = cwarps;
+            a.ksplit = 1;
+            double gatherSlots, builtEntries, phases;
+            int warps;
+            size_t smemFloats;
+            if (L->stride == 1) {
+              p.kernel = tc ? 2 : 0;
+              a.PW = L->Win + L->pad;
+              a.RI = R + L->ksz - 1;
+              a.pwarps = CeilDiv(R * a.PW, 32 * J);
+              a.rgroups = 1;
+              const int need1 = a.RI * a.PW + std::max(L->pad, L->ksz - 1) + 1;
+              const int need2 = a.pwarps * 32 * J + (L->ksz - 1) * a.PW + (L->ksz - 1) + 1;
+              warps = a.pwarps * cwarps;
+              if (tc) {
+                const int NM = RoundUp(std::max(need1, need2), 32);  // MMA N = LUT columns per subspace
+                if (NM > 256 || warps < 4) continue;
+                a.RI = NM;          // the tensor-core kernel receives NM in this field
+                a.PP = NM + 4;      // row pitch = 4 (mod 32) words: conflict-free 128-bit drains from TMEM
+                smemFloats = 128 * static_cast<size_t>(a.PP) + static_cast<size_t>(taps) * CT + 2048 + 25 * static_cast<size_t>(NM) + 1024 + 8;
+              } else {
+                a.PP = RoundUp(std::max(need1, need2), 4);
+                smemFloats = static_cast<size_t>(L->K) * a.PP + static_cast<size_t>(taps) * CT + 24 * static_cast<size_t>(L->K) + 17 * static_cast<size_t>(a.PP);
+              }
+              gatherSlots = static_cast<double>(a.pwarps) * J * taps * L->S * CT;   // wavefronts of LUT reads
+              builtEntries = static_cast<double>(a.PP) * L->K * L->S;
+              phases = L->S;
+            } else {
+              if (tc) continue;
+              p.kernel = 1;
+              a.rgroups = CeilDiv(L->ksz, L->stride);
+              a.pwarps = CeilDiv(L->Wo, 32 * J);
+              const int ph1 = CeilDiv(L->Win + 2 * L->pad, L->stride);
+              const int ph2 = a.pwarps * 32 * J + (L->ksz - 1) / L->stride + 1;
+              a.PW = std::max(ph1, ph2);           // phase length
+              a.PP = RoundUp(a.PW * L->stride, 4);
+              a.RI = 0;
+              warps = a.pwarps * cwarps * a.rgroups;
+              const double rowsIn = (R - 1) * L->stride + L->ksz;
+              gatherSlots = static_cast<double>(a.pwarps) * J * R * taps * L->S * CT;
+              builtEntries = static_cast<double>(a.PP) * L->K * L->S * rowsIn;
+              phases = L->S * rowsIn;
+              smemFloats = static_cast<size_t>(L->K) * a.PP + static_cast<size_t>(taps) * CT + 24 * static_cast<size_t>(L->K) + 17 * static_cast<size_t>(a.PP);
+            }
+            p.CPT = CPT; p.J = J;
+            p.threads = warps * 32;
+            if (p.threads > kMaxThreads || p.threads < 64) continue;
+            // FFMA path: lut + idx + cb2 + xs[2] + posoff + cbN; tensor path: lut + idx + A/B tiles + raw staging
+            p.smem = sizeof(float) * smemFloats + RoundUp(taps * CT, 16);
+            if (p.smem > smemMax) continue;
+            // measured on B200 (profiles/): ~1.3 clk per gather wavefront; FFMA LUT stage ~0.12 clk per entry at d = 8;
+            // tensor-core LUT stage: the MMA is hidden behind the gather, what remains is the TMEM drain + operand split
+            const double gather = gatherSlots * (1.0 + 1.0 / (4.0 * J)) * 1.3;
+            const double build = tc ? builtEntries * 0.02 + 300.0 * phases : builtEntries * ipe / 5.5 * 0.12;
+            const double perCta = gather + build + 400.0 * phases;
+            // few resident warps cannot keep ~30 LDS in flight per SM nor feed the FMA pipe during the LUT stage
+            // (measured: 2-warp CTAs run the build at ~0.5 IPC); 64 accumulators at 512 threads spill
+            double occPenalty = warps < 4 ? 2.5 : (warps < 6 ? 1.6 : (warps < 8 ? 1.25 : 1.0));
+            if (p.threads > 384 && J * CPT >= 64) occPenalty *= 1.1;
+            const double ctas = static_cast<double>(G) * nct * a.nstrips * N;
+            const double waves = std::ceil(ctas / L->ctx->sm_count);
+            const double cost = perCta * waves * occPenalty;
+            if (cost < bestCost) { bestCost = cost; best = p; found = true; }
           }
-          p.CPT = CPT; p.J = J;
-          p.threads = warps * 32;
-          if (p.threads > kMaxThreads || p.threads < 64) continue;
-          // lut + idx + cb2 + xs[2] + posoff + cbN (floats) + idN (bytes)
-          p.smem = sizeof(float) * (static_cast<size_t>(L->K) * a.PP + static_cast<size_t>(taps) * CT +
-                                    24 * static_cast<size_t>(L->K) + 17 * static_cast<size_t>(a.PP)) +
-                   RoundUp(taps * CT, 16);
-          if (p.smem > smemMax) continue;
-          // measured on B200 (profiles/): ~1.3 clk per gather wavefront, ~0.12 clk per LUT entry at d = 8
-          const double gather = gatherSlots * (1.0 + 1.0 / (4.0 * J)) * 1.3;
-          const double build = builtEntries * ipe / 5.5 * 0.12;
-          const double perCta = gather + build + 400.0 * phases;
-          // few resident warps cannot keep ~30 LDS in flight per SM; 64 accumulators at 512 threads spill
-          double occPenalty = warps < 6 ? 1.3 : (warps < 8 ? 1.1 : 1.0);
-          if (p.threads > 384 && J * CPT >= 64) occPenalty *= 1.1;
-          const double ctas = static_cast<double>(G) * nct * a.nstrips * N;
-          const double waves = std::ceil(ctas / L->ctx->sm_count);
-          const double cost = perCta * waves * occPenalty;
-          if (cost < bestCost) { bestCost = cost; best = p; found = true; }
         }
       }
     }
@@ -619,7 +889,7 @@ int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   ConvArgs a = p.a;
   a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
   a.N = N; a.relu = relu; a.src_nchw = L->src_nchw;
-  QCNN_CHECK(!(a.src_nchw && p.kernel == 0), "qcnn_conv_aprx_forward: NCHW source is only supported by the strided kernel");
+  QCNN_CHECK(!(a.src_nchw && p.kernel != 1), "qcnn_conv_aprx_forward: NCHW source is only supported by the strided kernel");
   int rc = 1;
 #define QCNN_DISPATCH(C, JJ) if (p.CPT == C && p.J == JJ) rc = LaunchOne<C, JJ>(p, a, st); else
   QCNN_DISPATCH(32, 1) QCNN_DISPATCH(32, 2) QCNN_DISPATCH(16, 1) QCNN_DISPATCH(16, 2) QCNN_DISPATCH(16, 3)
@@ -634,7 +904,7 @@ int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
   if (int prc = PlanConv(L, N)) return prc;
   const ConvPlan& p = L->plan;
   snprintf(buf, cap, "%s CPT=%d J=%d threads=%d smem=%zuB grid=(%d,%d) R=%d strips=%d CT=%d nct=%d PP=%d pwarps=%d "
-           "cwarps=%d rgroups=%d", p.kernel == 0 ? "conv_s1" : "conv_roll", p.CPT, p.J, p.threads, p.smem,
+           "cwarps=%d rgroups=%d", p.kernel == 0 ? "conv_s1" : (p.kernel == 2 ? "conv_s1_tc(tcgen05 LUT)" : "conv_roll"), p.CPT, p.J, p.threads, p.smem,
            p.a.G * p.a.nct * p.a.nstrips, N, p.a.R, p.a.nstrips, p.a.CT, p.a.nct, p.a.PP, p.a.pwarps, p.a.cwarps,
            p.a.rgroups);
   return 0;

@@ -732,6 +732,210 @@ __global__ void __launch_bounds__(MAXT, 1) conv_roll_kernel(const ConvArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// rolling-row kernel, tensor-core LUT stage: same row-group structure as conv_roll_kernel; the LUT of the NEXT
+// (input row, subspace) step is produced by tcgen05.mma into TMEM while the CUDA cores gather the current one.
+// ------------------------------------------------------------------------------------------------------------
+template <int CPT, int J, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) conv_roll_tc_kernel(const ConvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int taps = a.ksz * a.ksz;
+  const int NM = a.RI;  // MMA N (multiple of 32, <= 256)
+  const SmemLayoutTc sm = CarveTc(smem, a.PP, NM, taps, a.CT);
+
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+  const int rg = warp % a.rgroups;
+  const int rest = warp / a.rgroups;
+  const int pw = rest % a.pwarps, cw = rest / a.pwarps;
+  int b = blockIdx.x;
+  const int strip = b % a.nstrips; b /= a.nstrips;
+  const int ct = b % a.nct;
+  const int g = b / a.nct;
+  const int n = blockIdx.y;
+  const int ho0 = strip * a.R;
+  const int ho_end = min(a.Ho, ho0 + a.R);
+  const int PH = a.PW;
+  const int wo0 = pw * 32 * J + lane;
+  const int cbase = ct * a.CT + cw * CPT;
+  const size_t chStride = a.src_nchw ? static_cast<size_t>(a.Hi) * a.Wi : 1;
+  const int pixStride = a.src_nchw ? 1 : a.Cin;
+  const size_t rowStride = static_cast<size_t>(a.Wi) * pixStride;
+  const float* src = a.src + static_cast<size_t>(n) * a.Hi * a.Wi * a.Cin + static_cast<size_t>(g) * a.Cg * chStride;
+  const uint8_t* asmtG = a.asmt + static_cast<size_t>(g) * a.S * taps * a.KgPad + ct * a.CT;
+
+  for (int pos = tid; pos < NM; pos += T) {
+    const int phase = pos / PH, i = pos - phase * PH;
+    const int wi = i * a.stride + phase - a.pad;
+    sm.posoff[pos] = (phase < a.stride && wi >= 0 && wi < a.Wi) ? wi * pixStride : -1;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(sm.tmemBase)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemU32(sm.mbar)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  float bias[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; c++) bias[c] = __ldg(a.bias + g * a.Kg + cbase + c);
+  Acc<CPT, J> acc;
+  acc.Fill(bias);
+  int ho_cur = ho0 + rg;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmemD = *sm.tmemBase;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NM >> 3) << 17) | (8u << 24);
+  const uint32_t rowBytes = static_cast<uint32_t>(a.PP) * 4u;
+
+  const int hi_begin = ho0 * a.stride - a.pad;
+  const int hi_end = (ho_end - 1) * a.stride - a.pad + a.ksz;
+  const int hi_lo = max(hi_begin, 0), hi_hi = min(hi_end, a.Hi);
+  const int steps = (hi_hi - hi_lo) * a.S;
+
+  auto fetchRaw = [&](int step) {  // step = (hi - hi_lo) * S + s
+    const int hi = hi_lo + step / a.S, s = step % a.S;
+    const int nj = max(0, min(8, min(a.Cg - s * a.d, a.d)));
+    const float* cg = a.ctrd + static_cast<size_t>(s) * 128 * a.d;
+    for (int e = tid; e < 1024; e += T) {
+      const int k = e >> 3, jj = e & 7;
+      CpAsync4(sm.cr + e, cg + (jj < nj ? k * a.d + jj : 0), jj < nj);
+    }
+    const float* rowp = src + hi * rowStride;
+    const int ch0 = s * a.d;
+    for (int e = tid; e < NM * 8; e += T) {
+      const int pos = e >> 3, jj = e & 7;
+      const int off = sm.posoff[pos];
+      const bool ok = off >= 0 && jj < nj;
+      CpAsync4(sm.xr + e, rowp + (ok ? off + (ch0 + jj) * chStride : 0), ok);
+    }
+  };
+  auto splitOperands = [&]() {
+    for (int e = tid; e < 1024; e += T) {
+      float hi, lo;
+      SplitTf32(sm.cr[e], hi, lo);
+      const int i = UmmaIdx(e >> 3, e & 7);
+      sm.aHi[i] = hi;
+      sm.aLo[i] = lo;
+    }
+    for (int e = tid; e < NM * 8; e += T) {
+      float hi, lo;
+      SplitTf32(sm.xr[e], hi, lo);
+      const int i = UmmaIdx(e >> 3, e & 7);
+      sm.bHi[i] = hi;
+      sm.bLo[i] = lo;
+    }
+  };
+  auto issueMma = [&]() {
+    const uint64_t dAh = UmmaDesc(sm.aHi), dAl = UmmaDesc(sm.aLo), dBh = UmmaDesc(sm.bHi), dBl = UmmaDesc(sm.bLo);
+    UmmaTf32(tmemD, dAh, dBh, idesc, 0);
+    UmmaTf32(tmemD, dAh, dBl, idesc, 1);
+    UmmaTf32(tmemD, dAl, dBh, idesc, 1);
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemU32(sm.mbar)) : "memory");
+  };
+
+  if (steps > 0) {
+    fetchRaw(0);
+    CpAsyncCommit();
+    CpAsyncWaitAll();
+    __syncthreads();
+    splitOperands();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) issueMma();
+    if (steps > 1) fetchRaw(1);
+    FetchOffsets(sm.idN, asmtG, taps, a.CT, a.KgPad, tid, T);
+    CpAsyncCommit();
+  }
+  int hi = hi_lo, s = 0;
+  for (int it = 0; it < steps; it++) {
+    const int kh = hi + a.pad - ho_cur * a.stride;  // warp-uniform
+    const bool active = ho_cur < ho_end && kh >= 0 && kh < a.ksz;
+    MbarWait(sm.mbar, it & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    CpAsyncWaitAll();
+    __syncthreads();  // (A)
+    {
+      const int q = warp & 3;
+      const int k = q * 32 + lane;
+      float* row = sm.lut + k * a.PP;
+      for (int c = warp >> 2; c < (NM >> 5); c += (nwarps + 3 - q) >> 2) {
+        uint32_t r[32];
+        const uint32_t taddr = tmemD + (static_cast<uint32_t>(q * 32) << 16) + c * 32;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                     "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+                       "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+                       "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+                       "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(row + c * 32 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+      }
+    }
+    if (a.S > 1 || it == 0) CommitOffsets(sm.idN, sm.idx, taps, a.CT, rowBytes, tid, T);
+    if (it + 1 < steps) splitOperands();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // (B)
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int hin = hi, sn = s + 1;
+    if (sn == a.S) { sn = 0; hin = hi + 1; }
+    if (it + 1 < steps) {
+      if (tid == 0) issueMma();
+      if (it + 2 < steps) fetchRaw(it + 2);
+      if (a.S > 1) FetchOffsets(sm.idN, asmtG + static_cast<size_t>(sn) * taps * a.KgPad, taps, a.CT, a.KgPad, tid, T);
+      CpAsyncCommit();
+    }
+    if (active) {
+      const char* lutq = reinterpret_cast<const char*>(sm.lut) + wo0 * 4;
+      const uint32_t* ip = sm.idx + (kh * a.ksz) * a.CT + cw * CPT;
+      for (int kw = 0; kw < a.ksz; kw++) {
+        const int phase = kw % a.stride, sh = kw / a.stride;
+        GatherTap<CPT, J>(acc, lutq + (phase * PH + sh) * 4, ip);
+        ip += a.CT;
+      }
+    }
+    if (s == a.S - 1 && ho_cur < ho_end && kh == a.ksz - 1) {
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        const int wo = wo0 + 32 * j;
+        if (wo < a.Wo) {
+          float* out = a.dst + ((static_cast<size_t>(n) * a.Ho + ho_cur) * a.Wo + wo) * a.Cout + g * a.Kg + cbase;
+          StoreChannels<CPT, J>(out, acc, j, a.relu);
+        }
+      }
+      acc.Fill(bias);
+      ho_cur += a.rgroups;
+    }
+    hi = hin; s = sn;
+  }
+  for (int h = max(hi_hi, hi_begin); h < hi_end; h++) {
+    const int kh = h + a.pad - ho_cur * a.stride;
+    if (ho_cur < ho_end && kh == a.ksz - 1) {
+#pragma unroll
+      for (int j = 0; j < J; j++) {
+        const int wo = wo0 + 32 * j;
+        if (wo < a.Wo) {
+          float* out = a.dst + ((static_cast<size_t>(n) * a.Ho + ho_cur) * a.Wo + wo) * a.Cout + g * a.Kg + cbase;
+          StoreChannels<CPT, J>(out, acc, j, a.relu);
+        }
+      }
+      acc.Fill(bias);
+      ho_cur += a.rgroups;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "r"(256) : "memory");
+}
+
 template <int CPT, int J, int MAXT>
 int LaunchBound(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
   dim3 grid(a.G * a.nct * a.nstrips, a.N);
@@ -741,6 +945,10 @@ int LaunchBound(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
     kern<<<grid, p.threads, p.smem, st>>>(a);
   } else if (p.kernel == 2) {
     auto kern = conv_s1_tc_kernel<CPT, J, MAXT>;
+    QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    kern<<<grid, p.threads, p.smem, st>>>(a);
+  } else if (p.kernel == 3) {
+    auto kern = conv_roll_tc_kernel<CPT, J, MAXT>;
     QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     kern<<<grid, p.threads, p.smem, st>>>(a);
   } else {
@@ -763,6 +971,8 @@ int LaunchOne(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
 
 namespace qcnn {
 
+constexpr size_t kMaxCand = 10;
+
 // Chooses the tiling of a conv layer for batch size N.  Cost model in SM-cycles per CTA, times the number of
 // waves the whole batch needs on this GPU (so small batches trade LUT rebuilds for parallelism):
 //   gather  = shared-memory wavefronts: one per (warp, tap, s, channel, position-slot) plus one 128-bit offset load
@@ -773,8 +983,7 @@ namespace qcnn {
 // The two stages do not overlap inside a CTA (one CTA per SM), so the costs add.
 int PlanConv(qcnn_layer* L, int N) {
   if (L->plan_N == N) return 0;
-  ConvPlan best;
-  double bestCost = 1e300;
+  std::vector<std::pair<double, ConvPlan>> cands;
   bool found = false;
   const int G = L->grp, Cg = L->Cin / G, Kg = L->Cout / G;
   const int taps = L->ksz * L->ksz;
@@ -783,7 +992,7 @@ int PlanConv(qcnn_layer* L, int N) {
   for (int s = 0; s < L->S; s++) dimsSum += std::max(0, std::min(Cg - s * L->d, L->d));
   const double ipe = 0.66 * (dimsSum / L->S) + 0.3;  // issue slots per LUT entry
   // tensor-core LUT stage: 128 codewords (MMA M), every subspace <= 8 dims (one K = 8 tf32 step); env QCNN_NO_TC=1 disables
-  const bool tcOk = L->stride == 1 && L->K == 128 && L->d <= 8 && getenv("QCNN_NO_TC") == nullptr;
+  const bool tcOk = L->K == 128 && L->d <= 8 && getenv("QCNN_NO_TC") == nullptr;
   const int cpts[2] = {32, 16};
   for (int ci = 0; ci < 2; ci++) {
     const int CPT = cpts[ci];
@@ -829,21 +1038,31 @@ int PlanConv(qcnn_layer* L, int N) {
               builtEntries = static_cast<double>(a.PP) * L->K * L->S;
               phases = L->S;
             } else {
-              if (tc) continue;
-              p.kernel = 1;
+              p.kernel = tc ? 3 : 1;
               a.rgroups = CeilDiv(L->ksz, L->stride);
               a.pwarps = CeilDiv(L->Wo, 32 * J);
               const int ph1 = CeilDiv(L->Win + 2 * L->pad, L->stride);
               const int ph2 = a.pwarps * 32 * J + (L->ksz - 1) / L->stride + 1;
-              a.PW = std::max(ph1, ph2);           // phase length
-              a.PP = RoundUp(a.PW * L->stride, 4);
-              a.RI = 0;
               warps = a.pwarps * cwarps * a.rgroups;
               const double rowsIn = (R - 1) * L->stride + L->ksz;
+              if (tc) {
+                // phase length = the real columns only; idle lanes beyond Wo then read into the next phase's columns
+                // (valid shared memory, results discarded), so the row must hold (stride-1)*PH + lanes + shift entries
+                a.PW = ph1;
+                const int NM = RoundUp(std::max(ph1 * L->stride, (L->stride - 1) * ph1 + ph2), 32);
+                if (NM > 256 || warps < 4) continue;
+                a.RI = NM;
+                a.PP = NM + 4;
+                smemFloats = 128 * static_cast<size_t>(a.PP) + static_cast<size_t>(taps) * CT + 2048 + 25 * static_cast<size_t>(NM) + 1024 + 8;
+              } else {
+                a.PW = std::max(ph1, ph2);           // phase length
+                a.PP = RoundUp(a.PW * L->stride, 4);
+                a.RI = 0;
+                smemFloats = static_cast<size_t>(L->K) * a.PP + static_cast<size_t>(taps) * CT + 24 * static_cast<size_t>(L->K) + 17 * static_cast<size_t>(a.PP);
+              }
               gatherSlots = static_cast<double>(a.pwarps) * J * R * taps * L->S * CT;
               builtEntries = static_cast<double>(a.PP) * L->K * L->S * rowsIn;
               phases = L->S * rowsIn;
-              smemFloats = static_cast<size_t>(L->K) * a.PP + static_cast<size_t>(taps) * CT + 24 * static_cast<size_t>(L->K) + 17 * static_cast<size_t>(a.PP);
             }
             p.CPT = CPT; p.J = J;
             p.threads = warps * 32;
@@ -853,7 +1072,8 @@ int PlanConv(qcnn_layer* L, int N) {
             if (p.smem > smemMax) continue;
             // measured on B200 (profiles/): ~1.3 clk per gather wavefront; FFMA LUT stage ~0.12 clk per entry at d = 8;
             // tensor-core LUT stage: the MMA is hidden behind the gather, what remains is the TMEM drain + operand split
-            const double gather = gatherSlots * (1.0 + 1.0 / (4.0 * J)) * 1.3;
+            // gather latency hiding improves with resident warps (9 warps: 1.37 clk/wavefront measured, 12: 1.28)
+            const double gather = gatherSlots * (1.0 + 1.0 / (4.0 * J)) * (1.15 + 1.6 / warps);
             const double build = tc ? builtEntries * 0.02 + 300.0 * phases : builtEntries * ipe / 5.5 * 0.12;
             const double perCta = gather + build + 400.0 * phases;
             // few resident warps cannot keep ~30 LDS in flight per SM nor feed the FMA pipe during the LUT stage
@@ -863,7 +1083,8 @@ int PlanConv(qcnn_layer* L, int N) {
             const double ctas = static_cast<double>(G) * nct * a.nstrips * N;
             const double waves = std::ceil(ctas / L->ctx->sm_count);
             const double cost = perCta * waves * occPenalty;
-            if (cost < bestCost) { bestCost = cost; best = p; found = true; }
+            cands.emplace_back(cost, p);
+            found = true;
           }
         }
       }
@@ -871,30 +1092,76 @@ int PlanConv(qcnn_layer* L, int N) {
   }
   QCNN_CHECK(found, "qcnn_conv_layer_create: no tiling fits (Cout/grp=%d must be a multiple of 16; K=%d must be a "
              "multiple of 8; k=%d, W=%d)", Kg, L->K, L->ksz, L->Win);
-  ConvArgs& a = best.a;
-  a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
-  a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = G; a.Cg = Cg; a.Kg = Kg;
-  a.KgPad = RoundUp(Kg, 16);
-  a.S = L->S; a.K = L->K; a.d = L->d;
+  // keep the kMaxCand cheapest tilings (by the model); LaunchConv times them on the device the first time a batch size
+  // is seen (QCNN_AUTOTUNE=0 keeps the model's first choice)
+  std::stable_sort(cands.begin(), cands.end(), [](const std::pair<double, ConvPlan>& x, const std::pair<double, ConvPlan>& y) { return x.first < y.first; });
+  if (!L->cands) L->cands = new std::vector<ConvPlan>();
+  L->cands->clear();
+  for (size_t i = 0; i < cands.size() && L->cands->size() < kMaxCand; i++) {
+    ConvPlan c = cands[i].second;
+    ConvArgs& a = c.a;
+    a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
+    a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = G; a.Cg = Cg; a.Kg = Kg;
+    a.KgPad = RoundUp(Kg, 16);
+    a.S = L->S; a.K = L->K; a.d = L->d;
+    // skip near-duplicates: same kernel/CPT/J/channel tiling and a strip count already present
+    bool dup = false;
+    for (const ConvPlan& e : *L->cands)
+      if (e.kernel == c.kernel && e.CPT == c.CPT && e.J == c.J && e.a.nct == c.a.nct && e.a.nstrips == c.a.nstrips) dup = true;
+    if (!dup) L->cands->push_back(c);
+  }
+  const ConvPlan best = (*L->cands)[0];
   L->plan = best;
   L->plan_N = N;
+  L->tuned = 0;
   return 0;
+}
+
+static int LaunchPlan(qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st) {
+  ConvArgs a = p.a;
+  a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
+  a.N = N; a.relu = relu; a.src_nchw = L->src_nchw;
+  QCNN_CHECK(!(a.src_nchw && (p.kernel == 0 || p.kernel == 2)), "qcnn_conv_aprx_forward: NCHW source is only supported by the strided kernel");
+  int rc = 1;
+#define QCNN_DISPATCH(C, JJ) if (p.CPT == C && p.J == JJ) rc = LaunchOne<C, JJ>(p, a, st); else
+  QCNN_DISPATCH(32, 1) QCNN_DISPATCH(32, 2) QCNN_DISPATCH(16, 1) QCNN_DISPATCH(16, 2) QCNN_DISPATCH(16, 3)
+  QCNN_DISPATCH(16, 4) { SetError("internal: no conv instantiation for CPT=%d J=%d", p.CPT, p.J); return 1; }
+#undef QCNN_DISPATCH
+  return rc;
 }
 
 int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st) {
   QCNN_CHECK(L->kind == QCNN_KIND_CONV, "qcnn_conv_aprx_forward: layer is not convolutional");
   QCNN_CHECK(N >= 1 && N <= 65535, "qcnn_conv_aprx_forward: N must be in [1, 65535] (got %d)", N);
   if (int prc = PlanConv(L, N)) return prc;
-  ConvPlan& p = L->plan;
-  ConvArgs a = p.a;
-  a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
-  a.N = N; a.relu = relu; a.src_nchw = L->src_nchw;
-  QCNN_CHECK(!(a.src_nchw && p.kernel != 1), "qcnn_conv_aprx_forward: NCHW source is only supported by the strided kernel");
-  int rc = 1;
-#define QCNN_DISPATCH(C, JJ) if (p.CPT == C && p.J == JJ) rc = LaunchOne<C, JJ>(p, a, st); else
-  QCNN_DISPATCH(32, 1) QCNN_DISPATCH(32, 2) QCNN_DISPATCH(16, 1) QCNN_DISPATCH(16, 2) QCNN_DISPATCH(16, 3)
-  QCNN_DISPATCH(16, 4) { SetError("internal: no conv instantiation for CPT=%d J=%d", p.CPT, p.J); return 1; }
-#undef QCNN_DISPATCH
+  // empirical choice among the model's best tilings: time each once on this device for this batch size
+  static const bool autotune = !(getenv("QCNN_AUTOTUNE") && getenv("QCNN_AUTOTUNE")[0] == '0');
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (autotune && !L->tuned && L->cands && L->cands->size() > 1 && cap == cudaStreamCaptureStatusNone) {
+    cudaEvent_t e0, e1;
+    QCNN_CUDA(cudaEventCreate(&e0));
+    QCNN_CUDA(cudaEventCreate(&e1));
+    float bestMs = 1e30f;
+    size_t bestI = 0;
+    for (size_t i = 0; i < L->cands->size(); i++) {
+      const ConvPlan& c = (*L->cands)[i];
+      if (LaunchPlan(L, c, src, N, dst, relu, st)) continue;   // warm-up (also sets the smem attribute)
+      QCNN_CUDA(cudaEventRecord(e0, st));
+      const int reps = N >= 64 ? 1 : 3;
+      for (int r = 0; r < reps; r++) LaunchPlan(L, c, src, N, dst, relu, st);
+      QCNN_CUDA(cudaEventRecord(e1, st));
+      if (cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); continue; }
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (ms < bestMs) { bestMs = ms; bestI = i; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    L->plan = (*L->cands)[bestI];
+    L->tuned = 1;
+  }
+  const int rc = LaunchPlan(L, L->plan, src, N, dst, relu, st);
   if (rc == 0) L->ctx->launches++;
   return rc;
 }
@@ -904,7 +1171,7 @@ int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
   if (int prc = PlanConv(L, N)) return prc;
   const ConvPlan& p = L->plan;
   snprintf(buf, cap, "%s CPT=%d J=%d threads=%d smem=%zuB grid=(%d,%d) R=%d strips=%d CT=%d nct=%d PP=%d pwarps=%d "
-           "cwarps=%d rgroups=%d", p.kernel == 0 ? "conv_s1" : (p.kernel == 2 ? "conv_s1_tc(tcgen05 LUT)" : "conv_roll"), p.CPT, p.J, p.threads, p.smem,
+           "cwarps=%d rgroups=%d", p.kernel == 0 ? "conv_s1" : (p.kernel == 2 ? "conv_s1_tc(tcgen05 LUT)" : (p.kernel == 3 ? "conv_roll_tc(tcgen05 LUT)" : "conv_roll")), p.CPT, p.J, p.threads, p.smem,
            p.a.G * p.a.nct * p.a.nstrips, N, p.a.R, p.a.nstrips, p.a.CT, p.a.nct, p.a.PP, p.a.pwarps, p.a.cwarps,
            p.a.rgroups);
   return 0;

@@ -106,6 +106,8 @@ struct qcnn_layer {
   // plans
   ConvPlan plan;
   int plan_N;            // batch size the cached plan was made for (0 = none)
+  int tuned;             // the plan for plan_N was confirmed by on-device timing
+  std::vector<ConvPlan>* cands;  // the model's best tilings for plan_N (autotune candidates)
   // FC scratch
   float* d_partial;
   size_t partial_bytes;

@@ -983,6 +983,9 @@ constexpr size_t kMaxCand = 10;
 // The two stages do not overlap inside a CTA (one CTA per SM), so the costs add.
 int PlanConv(qcnn_layer* L, int N) {
   if (L->plan_N == N) return 0;
+  if (L->tunedPlans)  // a batch size seen (and timed) before: reuse its plan
+    for (const std::pair<int, ConvPlan>& e : *L->tunedPlans)
+      if (e.first == N) { L->plan = e.second; L->plan_N = N; L->tuned = 1; return 0; }
   std::vector<std::pair<double, ConvPlan>> cands;
   bool found = false;
   const int G = L->grp, Cg = L->Cin / G, Kg = L->Cout / G;
@@ -1160,6 +1163,8 @@ int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
     cudaEventDestroy(e1);
     L->plan = (*L->cands)[bestI];
     L->tuned = 1;
+    if (!L->tunedPlans) L->tunedPlans = new std::vector<std::pair<int, ConvPlan>>();
+    L->tunedPlans->emplace_back(N, L->plan);
   }
   const int rc = LaunchPlan(L, L->plan, src, N, dst, relu, st);
   if (rc == 0) L->ctx->launches++;

@@ -250,6 +250,7 @@ void qcnn_layer_destroy(qcnn_layer* L) {
   if (L->d_partial) cudaFree(L->d_partial);
   if (L->d_srcoff) cudaFree(L->d_srcoff);
   delete L->cands;
+  delete L->tunedPlans;
   delete L;
 }
 

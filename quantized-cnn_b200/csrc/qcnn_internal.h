@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/qcnn.h"
@@ -108,6 +109,7 @@ struct qcnn_layer {
   int plan_N;            // batch size the cached plan was made for (0 = none)
   int tuned;             // the plan for plan_N was confirmed by on-device timing
   std::vector<ConvPlan>* cands;  // the model's best tilings for plan_N (autotune candidates)
+  std::vector<std::pair<int, ConvPlan>>* tunedPlans;  // timed winners per batch size
   // FC scratch
   float* d_partial;
   size_t partial_bytes;

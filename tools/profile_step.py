@@ -1,5 +1,5 @@
 """Minimal driver for ncu captures: builds the AlexNet PQ net and runs `--iters` forward passes at batch `--batch`.
-    ncu --set full --clock-control none --import-source on -k regex:'conv_|fc_aprx' -s <skip> -c <n> -o out \
+    ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'conv_|fc_aprx|lrn_' -o out \
         python tools/profile_step.py --batch 256 --iters 2
 """
 import argparse
@@ -30,9 +30,15 @@ def main():
         pl = net.pq_layer(l)
         if pl is not None:
             print("layer", l, pl.describe(args.batch))
-    for _ in range(args.iters):
+    # warm-up passes (also lets the conv tilings be autotuned); only the LAST pass is inside the profiler range:
+    #   ncu --profile-from-start off ... python tools/profile_step.py
+    for _ in range(max(args.iters - 1, 1)):
         net.forward(img, prob=prob)
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    net.forward(img, prob=prob)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
     print("done", what, float(prob[0].max()))
 
 

@@ -1,0 +1,123 @@
+"""Turns ncu captures brought back in gpurun_out/ into the small, committed summaries under profiles/.
+    python tools/summarize_profiles.py <full.ncu-rep> <launches.csv> <tag>
+full.ncu-rep : ncu --set full --clock-control none --import-source on ... tools/profile_step.py
+launches.csv : ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ... bench.py
+"""
+import collections
+import csv
+import io
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ncu_csv(rep, page):
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+
+def kernels_table(rep, out_path, title):
+    rows = ncu_csv(rep, "raw")
+    hdr = rows[0]
+    want = [("Kernel Name", "kernel"), ("Grid Size", "grid"), ("Block Size", "block"), ("gpu__time_duration.sum", "time_ms"),
+            ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "smem_dyn_KB"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
+            ("dram__bytes_read.sum", "dram_read_MB"), ("dram__bytes_write.sum", "dram_write_MB"),
+            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+            ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
+            ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
+            ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex_pct"),
+            ("sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+            ("sm__cycles_elapsed.avg", "sm_cycles")]
+    with open(out_path, "w") as f:
+        f.write("# " + title + "\n")
+        f.write(",".join(n for _, n in want) + "\n")
+        for r in rows[2:]:
+            vals = []
+            for k, n in want:
+                v = r[hdr.index(k)] if k in hdr else ""
+                if n == "kernel":
+                    v = v.replace("void <unnamed>::", "").replace("<unnamed>::", "").replace(",", ";")[:64]
+                vals.append('"%s"' % v)
+            f.write(",".join(vals) + "\n")
+
+
+def stage_split(rep, out_path, title):
+    """Per kernel: share of stall samples / instructions / shared-memory wavefronts between consecutive barriers
+    (== the staging / LUT / gather stages of the conv kernels)."""
+    rows = ncu_csv(rep, "source")
+    kern, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "hdr": None, "ins": []}
+            kern.append(cur)
+        elif r and r[0] == "Address" and cur is not None:
+            cur["hdr"] = r
+        elif cur and cur["hdr"] and len(r) >= 6:
+            cur["ins"].append(r)
+    seen = set()
+    with open(out_path, "w") as f:
+        f.write("# " + title + "\n")
+        for k in kern:
+            h = k["hdr"]
+            i_s, i_e, i_w = h.index("# Samples"), h.index("Instructions Executed"), h.index("L1 Wavefronts Shared")
+            tot = sum(int(r[i_s] or 0) for r in k["ins"])
+            tote = sum(int(r[i_e] or 0) for r in k["ins"])
+            if (k["name"], tot) in seen or tot == 0:
+                continue
+            seen.add((k["name"], tot))
+            sass = " ".join(r[1] for r in k["ins"])
+            f.write("\n## %s\nsamples %d, warp instructions %d; SASS has UTCHMMA: %s, LDTM: %s, LDGSTS: %s, FFMA2: %s, FADD2: %s\n" % (
+                k["name"].replace("void <unnamed>::", "")[:90], tot, tote, "UTCHMMA" in sass, "LDTM" in sass,
+                "LDGSTS" in sass, "FFMA2" in sass, "FADD2" in sass))
+            reg, regs = 0, collections.OrderedDict()
+            for r in k["ins"]:
+                op = r[1].strip().split()[0] if r[1].strip() else ""
+                if op.startswith("@") and len(r[1].strip().split()) > 1:
+                    op = r[1].strip().split()[1]
+                d = regs.setdefault(reg, {"s": 0, "e": 0, "w": 0, "ops": collections.Counter()})
+                d["s"] += int(r[i_s] or 0)
+                d["e"] += int(r[i_e] or 0)
+                d["w"] += int(r[i_w] or 0)
+                d["ops"][op.split(".")[0]] += int(r[i_e] or 0)
+                if op.startswith("BAR"):
+                    reg += 1
+            for rg, d in regs.items():
+                if d["s"] * 100 < tot:
+                    continue
+                top = ", ".join("%s %.0f%%" % (o, 100.0 * c / max(d["e"], 1)) for o, c in d["ops"].most_common(5))
+                f.write("- segment %d: %.1f%% of stall samples, %.1f%% of instructions, %d smem wavefronts | %s\n" % (
+                    rg, 100.0 * d["s"] / tot, 100.0 * d["e"] / max(tote, 1), d["w"], top))
+
+
+def launch_list(csv_path, out_path, title):
+    lines = [l for l in open(csv_path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except (KeyError, ValueError):
+            continue
+        k = row["Kernel Name"].replace("void <unnamed>::", "").replace("<unnamed>::", "")[:60]
+        agg.setdefault((k, row.get("Grid Size", ""), row.get("Block Size", "")), []).append(v)
+    tot = sum(sum(v) for v in agg.values())
+    with open(out_path, "w") as f:
+        f.write("# " + title + "\n# per-launch device time is cold-cache and serialised under ncu: compare SHARES\n")
+        f.write("kernel,grid,block,launches,total_us,share_pct,avg_us\n")
+        for (k, g, b), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write('"%s","%s","%s",%d,%.1f,%.2f,%.1f\n' % (k.replace(",", ";"), g, b, len(v), sum(v) / 1e3, 100 * sum(v) / tot, sum(v) / len(v) / 1e3))
+
+
+if __name__ == "__main__":
+    rep, launches, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    kernels_table(rep, os.path.join(ROOT, "profiles", "%s_ncu_full_b256.csv" % tag),
+                  "ncu --set full --clock-control none --import-source on; tools/profile_step.py --batch 256 (AlexNet PQ forward)")
+    stage_split(rep, os.path.join(ROOT, "profiles", "%s_stage_split_b256.md" % tag),
+                "Where the time goes inside each kernel (stall samples between barriers), from the same capture")
+    if launches and os.path.exists(launches):
+        launch_list(launches, os.path.join(ROOT, "profiles", "%s_launches_bench.csv" % tag),
+                    "ncu --metrics gpu__time_duration.sum --clock-control none; python bench.py --steps 2 --warmup 1")

@@ -936,6 +936,154 @@ __global__ void __launch_bounds__(MAXT, 1) conv_roll_tc_kernel(const ConvArgs a)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "r"(256) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// single-subspace, narrow-subspace layers (AlexNet conv1: S = 1, 3 of the 8 codebook dims exist).
+// With S = 1 every LUT entry  LUT[pixel][k] = <x_pixel, c_k>  would be read only ~ (k/stride)^2 * Cout / K ~ 5 times,
+// so tabulating costs more than it saves.  This kernel keeps the layer in PQ form (codebook + uint8 assignments) but
+// evaluates the inner product where it is consumed:  acc[p][c] += <x[p + tap], c_{asmt[tap][c]}>  -- the same sum,
+// the codeword (not the partial product) is what the warp-uniform assignment index gathers (128-bit broadcast load).
+// A thread owns 2 output rows x 2 columns x CPT channels (float2 pairs, FFMA2); the strip's input rows live in shared
+// memory, de-interleaved by stride phase, so a tap is a constant shift and there are no barriers after the tile load.
+// ------------------------------------------------------------------------------------------------------------
+template <int CPT, int NJ>
+__global__ void __launch_bounds__(512, 1) conv_direct_kernel(const ConvArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int taps = a.ksz * a.ksz;
+  const int PH = a.PW, PITCH = a.PP;                // phase length, padded row pitch (floats)
+  const int rowsIn = (a.R - 1) * a.stride + a.ksz;  // input rows of the strip
+  float* xin = reinterpret_cast<float*>(smem);                                   // [rowsIn][NJ][PITCH]
+  float2* cb = reinterpret_cast<float2*>(xin + static_cast<size_t>(rowsIn) * NJ * PITCH + 64);  // [K][4] (c,c) pairs
+  uint32_t* idxa = reinterpret_cast<uint32_t*>(cb + a.K * 4);                    // [taps][CT] smem address of cb[k]
+
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int cw = warp % a.cwarps, rw = warp / a.cwarps;   // channel warp, row-pair warp
+  int b = blockIdx.x;
+  const int strip = b % a.nstrips; b /= a.nstrips;
+  const int ct = b % a.nct;
+  const int g = b / a.nct;
+  const int n = blockIdx.y;
+  const int ho0 = strip * a.R;
+  const int ho_end = min(a.Ho, ho0 + a.R);
+  const int cbase = ct * a.CT + cw * CPT;
+  const size_t chStride = a.src_nchw ? static_cast<size_t>(a.Hi) * a.Wi : 1;
+  const int pixStride = a.src_nchw ? 1 : a.Cin;
+  const size_t rowStride = static_cast<size_t>(a.Wi) * pixStride;
+  const float* src = a.src + static_cast<size_t>(n) * a.Hi * a.Wi * a.Cin + static_cast<size_t>(g) * a.Cg * chStride;
+  const int nj = min(NJ, min(a.Cg, a.d));
+  const int hi0 = ho0 * a.stride - a.pad;
+
+  // input tile: element (row r, dim jj, column position) <- pixel (hi0 + r, wi), zero outside the image
+  for (int e = tid; e < rowsIn * NJ * PITCH; e += T) {
+    const int pos = e % PITCH;
+    const int rj = e / PITCH;
+    const int jj = rj % NJ, r = rj / NJ;
+    const int phase = pos / PH, i = pos - phase * PH;
+    const int wi = i * a.stride + phase - a.pad;
+    const int hi = hi0 + r;
+    const bool ok = phase < a.stride && wi >= 0 && wi < a.Wi && hi >= 0 && hi < a.Hi && jj < nj;
+    CpAsync4(xin + e, src + (ok ? hi * rowStride + static_cast<size_t>(wi) * pixStride + jj * chStride : 0), ok);
+  }
+  CpAsyncCommit();
+  for (int e = tid; e < a.K * 4; e += T) {
+    const int k = e >> 2, jj = e & 3;
+    const float c = (jj < nj) ? __ldg(a.ctrd + static_cast<size_t>(k) * a.d + jj) : 0.0f;
+    cb[e] = make_float2(c, c);
+  }
+  {
+    const uint8_t* ap = a.asmt + static_cast<size_t>(g) * taps * a.KgPad + ct * a.CT;  // S == 1
+    const uint32_t cbBase = static_cast<uint32_t>(__cvta_generic_to_shared(cb));
+    for (int e = tid; e < taps * a.CT; e += T) {
+      const int tap = e / a.CT, c = e - tap * a.CT;
+      idxa[e] = cbBase + static_cast<uint32_t>(__ldg(ap + tap * a.KgPad + c)) * 32u;
+    }
+  }
+  float bias[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; c++) bias[c] = __ldg(a.bias + g * a.Kg + cbase + c);
+  CpAsyncWaitAll();
+  __syncthreads();
+
+  const int pairs = (ho_end - ho0 + 1) >> 1;
+  for (int pr = rw; pr < pairs; pr += a.rgroups) {
+    const int ra = 2 * pr;                       // strip-local output rows ra, ra + 1
+    const bool hasB = ho0 + ra + 1 < ho_end;
+    float2 accA[CPT], accB[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; c++) { accA[c] = make_float2(bias[c], bias[c]); accB[c] = accA[c]; }
+    for (int kh = 0; kh < a.ksz; kh++) {
+      const float* rowA = xin + static_cast<size_t>(ra * a.stride + kh) * NJ * PITCH + lane;
+      const float* rowB = rowA + static_cast<size_t>(hasB ? a.stride : 0) * NJ * PITCH;
+      const uint32_t* ip = idxa + (kh * a.ksz) * a.CT + cw * CPT;
+      for (int kw = 0; kw < a.ksz; kw++) {
+        const int shift = (kw % a.stride) * PH + kw / a.stride;
+        float2 xa[NJ], xb[NJ];
+#pragma unroll
+        for (int jj = 0; jj < NJ; jj++) {
+          xa[jj] = make_float2(rowA[jj * PITCH + shift], rowA[jj * PITCH + shift + 32]);
+          xb[jj] = make_float2(rowB[jj * PITCH + shift], rowB[jj * PITCH + shift + 32]);
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < CPT; c4 += 4) {
+          const uint4 ad = *reinterpret_cast<const uint4*>(ip + c4);
+          const uint32_t adr[4] = {ad.x, ad.y, ad.z, ad.w};
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            float4 c01;
+            float2 c2 = make_float2(0.f, 0.f), c3 = make_float2(0.f, 0.f);
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c01.x), "=f"(c01.y), "=f"(c01.z), "=f"(c01.w) : "r"(adr[u]));
+            if (NJ > 2) {
+              if (NJ > 3) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(c2.x), "=f"(c2.y), "=f"(c3.x), "=f"(c3.y) : "r"(adr[u]));
+              else asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+16];" : "=f"(c2.x), "=f"(c2.y) : "r"(adr[u]));
+            }
+            const int c = c4 + u;
+            accA[c] = __ffma2_rn(make_float2(c01.x, c01.y), xa[0], accA[c]);
+            accB[c] = __ffma2_rn(make_float2(c01.x, c01.y), xb[0], accB[c]);
+            if (NJ > 1) {
+              accA[c] = __ffma2_rn(make_float2(c01.z, c01.w), xa[1 % NJ], accA[c]);
+              accB[c] = __ffma2_rn(make_float2(c01.z, c01.w), xb[1 % NJ], accB[c]);
+            }
+            if (NJ > 2) {
+              accA[c] = __ffma2_rn(c2, xa[2 % NJ], accA[c]);
+              accB[c] = __ffma2_rn(c2, xb[2 % NJ], accB[c]);
+            }
+            if (NJ > 3) {
+              accA[c] = __ffma2_rn(c3, xa[3 % NJ], accA[c]);
+              accB[c] = __ffma2_rn(c3, xb[3 % NJ], accB[c]);
+            }
+          }
+        }
+        ip += a.CT;
+      }
+    }
+    // emit rows ra (and ra + 1): lanes hold columns lane and lane + 32
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int wo = lane + 32 * half;
+      if (wo < a.Wo) {
+        float* outA = a.dst + ((static_cast<size_t>(n) * a.Ho + ho0 + ra) * a.Wo + wo) * a.Cout + g * a.Kg + cbase;
+#pragma unroll
+        for (int c = 0; c < CPT; c += 4) {
+          float4 o = half ? make_float4(accA[c].y, accA[c + 1].y, accA[c + 2].y, accA[c + 3].y)
+                          : make_float4(accA[c].x, accA[c + 1].x, accA[c + 2].x, accA[c + 3].x);
+          if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          *reinterpret_cast<float4*>(outA + c) = o;
+        }
+        if (hasB) {
+          float* outB = outA + static_cast<size_t>(a.Wo) * a.Cout;
+#pragma unroll
+          for (int c = 0; c < CPT; c += 4) {
+            float4 o = half ? make_float4(accB[c].y, accB[c + 1].y, accB[c + 2].y, accB[c + 3].y)
+                            : make_float4(accB[c].x, accB[c + 1].x, accB[c + 2].x, accB[c + 3].x);
+            if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(outB + c) = o;
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int CPT, int J, int MAXT>
 int LaunchBound(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
   dim3 grid(a.G * a.nct * a.nstrips, a.N);
@@ -971,7 +1119,7 @@ int LaunchOne(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
 
 namespace qcnn {
 
-constexpr size_t kMaxCand = 10;
+constexpr size_t kMaxCand = 12;
 
 // Chooses the tiling of a conv layer for batch size N.  Cost model in SM-cycles per CTA, times the number of
 // waves the whole batch needs on this GPU (so small batches trade LUT rebuilds for parallelism):
@@ -1093,6 +1241,45 @@ int PlanConv(qcnn_layer* L, int N) {
       }
     }
   }
+  // single subspace of <= 4 existing dims: evaluate <x, codeword> at the point of use (conv_direct_kernel)
+  if (L->S == 1 && std::min(Cg, L->d) <= 4 && L->Wo <= 64 && getenv("QCNN_NO_DIRECT") == nullptr) {
+    const int NJ = std::min(Cg, L->d) <= 3 ? 3 : 4;
+    const int dcpts[2] = {16, 8};
+    for (int ci = 0; ci < 2; ci++) {
+      const int CPT = dcpts[ci];
+      if (Kg % CPT != 0 || Kg % 16 != 0) continue;
+      for (int nct = 1; nct <= 2; nct++) {
+        if (Kg % nct != 0 || (Kg / nct) % 16 != 0 || (Kg / nct) % CPT != 0) continue;
+        const int CT = Kg / nct, cwarps = CT / CPT;
+        for (int R = 2; R <= L->Ho + 1; R += 2) {
+          for (int rgroups = 1; rgroups <= 4; rgroups++) {
+            ConvPlan p;
+            memset(&p, 0, sizeof(p));
+            ConvArgs& a = p.a;
+            p.kernel = 4; p.CPT = CPT; p.J = 2;
+            a.R = std::min(R, L->Ho + (L->Ho & 1)); a.nstrips = CeilDiv(L->Ho, a.R);
+            a.CT = CT; a.nct = nct; a.cwarps = cwarps; a.pwarps = 1; a.rgroups = rgroups; a.ksplit = 1;
+            a.PW = CeilDiv(L->Win + 2 * L->pad, L->stride);       // phase length
+            a.PP = RoundUp(a.PW * L->stride, 4);                   // row pitch
+            p.threads = 32 * cwarps * rgroups;
+            if (p.threads > 512 || p.threads < 128) continue;
+            const int rowsIn = (a.R - 1) * L->stride + L->ksz;
+            p.smem = sizeof(float) * (static_cast<size_t>(rowsIn) * NJ * a.PP + 64 + 8 * static_cast<size_t>(L->K) +
+                                      static_cast<size_t>(taps) * CT);
+            if (p.smem > smemMax) continue;
+            const int pairs = a.R / 2;
+            // issue slots: per (row pair, tap, channel) 2 loads + 2*NJ FFMA2, plus 4*NJ pixel loads per tap
+            const double perWarp = static_cast<double>(CeilDiv(pairs, rgroups)) * taps * (CPT * (2.0 + 2.0 * NJ) + 4.0 * NJ + CPT / 4.0);
+            const double perCta = perWarp * cwarps * rgroups / 2.6 + rowsIn * NJ * a.PP * 0.5;
+            const double ctas = static_cast<double>(G) * nct * a.nstrips * N;
+            const double waves = std::ceil(ctas / L->ctx->sm_count);
+            cands.emplace_back(perCta * waves, p);
+            found = true;
+          }
+        }
+      }
+    }
+  }
   QCNN_CHECK(found, "qcnn_conv_layer_create: no tiling fits (Cout/grp=%d must be a multiple of 16; K=%d must be a "
              "multiple of 8; k=%d, W=%d)", Kg, L->K, L->ksz, L->Win);
   // keep the kMaxCand cheapest tilings (by the model); LaunchConv times them on the device the first time a batch size
@@ -1100,19 +1287,42 @@ int PlanConv(qcnn_layer* L, int N) {
   std::stable_sort(cands.begin(), cands.end(), [](const std::pair<double, ConvPlan>& x, const std::pair<double, ConvPlan>& y) { return x.first < y.first; });
   if (!L->cands) L->cands = new std::vector<ConvPlan>();
   L->cands->clear();
-  for (size_t i = 0; i < cands.size() && L->cands->size() < kMaxCand; i++) {
-    ConvPlan c = cands[i].second;
-    ConvArgs& a = c.a;
-    a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
-    a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = G; a.Cg = Cg; a.Kg = Kg;
-    a.KgPad = RoundUp(Kg, 16);
-    a.S = L->S; a.K = L->K; a.d = L->d;
-    // skip near-duplicates: same kernel/CPT/J/channel tiling and a strip count already present
-    bool dup = false;
-    for (const ConvPlan& e : *L->cands)
-      if (e.kernel == c.kernel && e.CPT == c.CPT && e.J == c.J && e.a.nct == c.a.nct && e.a.nstrips == c.a.nstrips) dup = true;
-    if (!dup) L->cands->push_back(c);
+  // QCNN_FORCE_KERNEL=<0 s1 | 1 roll | 2 s1_tc | 3 roll_tc | 4 direct> restricts the choice (tests / experiments)
+  const char* force = getenv("QCNN_FORCE_KERNEL");
+  if (force) {
+    std::vector<std::pair<double, ConvPlan>> kept;
+    for (const auto& c : cands) if (c.second.kernel == atoi(force)) kept.push_back(c);
+    if (!kept.empty()) cands.swap(kept);
   }
+  // every kernel family that has a feasible tiling gets at least two seats among the candidates
+  for (int pass = 0; pass < 2; pass++) {
+    int perKernel[5] = {0, 0, 0, 0, 0};
+    for (size_t i = 0; i < cands.size() && L->cands->size() < kMaxCand; i++) {
+      ConvPlan c = cands[i].second;
+      if (pass == 0 && perKernel[c.kernel] >= 2) continue;
+      ConvArgs& a = c.a;
+      a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
+      a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = G; a.Cg = Cg; a.Kg = Kg;
+      a.KgPad = RoundUp(Kg, 16);
+      a.S = L->S; a.K = L->K; a.d = L->d;
+      // skip near-duplicates: same kernel/CPT/J/channel tiling and a strip count already present
+      bool dup = false;
+      for (const ConvPlan& e : *L->cands)
+        if (e.kernel == c.kernel && e.CPT == c.CPT && e.J == c.J && e.a.nct == c.a.nct && e.a.nstrips == c.a.nstrips &&
+            e.a.rgroups == c.a.rgroups) dup = true;
+      if (dup) continue;
+      L->cands->push_back(c);
+      perKernel[c.kernel]++;
+    }
+  }
+  // the model's overall favourite first (it is the plan used when autotuning is off)
+  for (size_t i = 1; i < L->cands->size(); i++)
+    if ((*L->cands)[i].kernel == cands[0].second.kernel && (*L->cands)[i].CPT == cands[0].second.CPT &&
+        (*L->cands)[i].J == cands[0].second.J && (*L->cands)[i].a.nct == cands[0].second.a.nct &&
+        (*L->cands)[i].a.nstrips == cands[0].second.a.nstrips && (*L->cands)[i].a.rgroups == cands[0].second.a.rgroups) {
+      std::swap((*L->cands)[0], (*L->cands)[i]);
+      break;
+    }
   const ConvPlan best = (*L->cands)[0];
   L->plan = best;
   L->plan_N = N;
@@ -1120,10 +1330,25 @@ int PlanConv(qcnn_layer* L, int N) {
   return 0;
 }
 
+template <int CPT, int NJ>
+static int LaunchDirect(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
+  dim3 grid(a.G * a.nct * a.nstrips, a.N);
+  auto kern = conv_direct_kernel<CPT, NJ>;
+  QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  kern<<<grid, p.threads, p.smem, st>>>(a);
+  QCNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int LaunchPlan(qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st) {
   ConvArgs a = p.a;
   a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
   a.N = N; a.relu = relu; a.src_nchw = L->src_nchw;
+  if (p.kernel == 4) {
+    const int nj = std::min(a.Cg, a.d);
+    if (p.CPT == 16) return nj <= 3 ? LaunchDirect<16, 3>(p, a, st) : LaunchDirect<16, 4>(p, a, st);
+    return nj <= 3 ? LaunchDirect<8, 3>(p, a, st) : LaunchDirect<8, 4>(p, a, st);
+  }
   QCNN_CHECK(!(a.src_nchw && (p.kernel == 0 || p.kernel == 2)), "qcnn_conv_aprx_forward: NCHW source is only supported by the strided kernel");
   int rc = 1;
 #define QCNN_DISPATCH(C, JJ) if (p.CPT == C && p.J == JJ) rc = LaunchOne<C, JJ>(p, a, st); else
@@ -1176,7 +1401,7 @@ int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
   if (int prc = PlanConv(L, N)) return prc;
   const ConvPlan& p = L->plan;
   snprintf(buf, cap, "%s CPT=%d J=%d threads=%d smem=%zuB grid=(%d,%d) R=%d strips=%d CT=%d nct=%d PP=%d pwarps=%d "
-           "cwarps=%d rgroups=%d", p.kernel == 0 ? "conv_s1" : (p.kernel == 2 ? "conv_s1_tc(tcgen05 LUT)" : (p.kernel == 3 ? "conv_roll_tc(tcgen05 LUT)" : "conv_roll")), p.CPT, p.J, p.threads, p.smem,
+           "cwarps=%d rgroups=%d", p.kernel == 0 ? "conv_s1" : (p.kernel == 2 ? "conv_s1_tc(tcgen05 LUT)" : (p.kernel == 3 ? "conv_roll_tc(tcgen05 LUT)" : (p.kernel == 4 ? "conv_direct" : "conv_roll"))), p.CPT, p.J, p.threads, p.smem,
            p.a.G * p.a.nct * p.a.nstrips, N, p.a.R, p.a.nstrips, p.a.CT, p.a.nct, p.a.PP, p.a.pwarps, p.a.cwarps,
            p.a.rgroups);
   return 0;

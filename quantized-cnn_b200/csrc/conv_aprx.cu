@@ -945,8 +945,8 @@ __global__ void __launch_bounds__(MAXT, 1) conv_roll_tc_kernel(const ConvArgs a)
 // A thread owns 2 output rows x 2 columns x CPT channels (float2 pairs, FFMA2); the strip's input rows live in shared
 // memory, de-interleaved by stride phase, so a tap is a constant shift and there are no barriers after the tile load.
 // ------------------------------------------------------------------------------------------------------------
-template <int CPT, int NJ>
-__global__ void __launch_bounds__(512, 1) conv_direct_kernel(const ConvArgs a) {
+template <int CPT, int NJ, int ROWS>
+__global__ void __launch_bounds__(384, 1) conv_direct_kernel(const ConvArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int taps = a.ksz * a.ksz;
   const int PH = a.PW, PITCH = a.PP;                // phase length, padded row pitch (floats)
@@ -1004,25 +1004,28 @@ __global__ void __launch_bounds__(512, 1) conv_direct_kernel(const ConvArgs a) {
   CpAsyncWaitAll();
   __syncthreads();
 
-  const int pairs = (ho_end - ho0 + 1) >> 1;
-  for (int pr = rw; pr < pairs; pr += a.rgroups) {
-    const int ra = 2 * pr;                       // strip-local output rows ra, ra + 1
-    const bool hasB = ho0 + ra + 1 < ho_end;
-    float2 accA[CPT], accB[CPT];
+  const int groups = (ho_end - ho0 + ROWS - 1) / ROWS;
+  for (int gr = rw; gr < groups; gr += a.rgroups) {
+    const int ra = ROWS * gr;                    // strip-local output rows ra .. ra + ROWS - 1
+    float2 acc[ROWS][CPT];
 #pragma unroll
-    for (int c = 0; c < CPT; c++) { accA[c] = make_float2(bias[c], bias[c]); accB[c] = accA[c]; }
+    for (int r = 0; r < ROWS; r++)
+#pragma unroll
+      for (int c = 0; c < CPT; c++) acc[r][c] = make_float2(bias[c], bias[c]);
+    int rowOff[ROWS];                            // rows past the strip re-read row ra (results discarded)
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) rowOff[r] = (ho0 + ra + r < ho_end ? r * a.stride : 0) * NJ * PITCH;
     for (int kh = 0; kh < a.ksz; kh++) {
       const float* rowA = xin + static_cast<size_t>(ra * a.stride + kh) * NJ * PITCH + lane;
-      const float* rowB = rowA + static_cast<size_t>(hasB ? a.stride : 0) * NJ * PITCH;
       const uint32_t* ip = idxa + (kh * a.ksz) * a.CT + cw * CPT;
       for (int kw = 0; kw < a.ksz; kw++) {
         const int shift = (kw % a.stride) * PH + kw / a.stride;
-        float2 xa[NJ], xb[NJ];
+        float2 x[ROWS][NJ];
 #pragma unroll
-        for (int jj = 0; jj < NJ; jj++) {
-          xa[jj] = make_float2(rowA[jj * PITCH + shift], rowA[jj * PITCH + shift + 32]);
-          xb[jj] = make_float2(rowB[jj * PITCH + shift], rowB[jj * PITCH + shift + 32]);
-        }
+        for (int r = 0; r < ROWS; r++)
+#pragma unroll
+          for (int jj = 0; jj < NJ; jj++)
+            x[r][jj] = make_float2(rowA[rowOff[r] + jj * PITCH + shift], rowA[rowOff[r] + jj * PITCH + shift + 32]);
 #pragma unroll
         for (int c4 = 0; c4 < CPT; c4 += 4) {
           const uint4 ad = *reinterpret_cast<const uint4*>(ip + c4);
@@ -1037,46 +1040,33 @@ __global__ void __launch_bounds__(512, 1) conv_direct_kernel(const ConvArgs a) {
               else asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+16];" : "=f"(c2.x), "=f"(c2.y) : "r"(adr[u]));
             }
             const int c = c4 + u;
-            accA[c] = __ffma2_rn(make_float2(c01.x, c01.y), xa[0], accA[c]);
-            accB[c] = __ffma2_rn(make_float2(c01.x, c01.y), xb[0], accB[c]);
-            if (NJ > 1) {
-              accA[c] = __ffma2_rn(make_float2(c01.z, c01.w), xa[1 % NJ], accA[c]);
-              accB[c] = __ffma2_rn(make_float2(c01.z, c01.w), xb[1 % NJ], accB[c]);
-            }
-            if (NJ > 2) {
-              accA[c] = __ffma2_rn(c2, xa[2 % NJ], accA[c]);
-              accB[c] = __ffma2_rn(c2, xb[2 % NJ], accB[c]);
-            }
-            if (NJ > 3) {
-              accA[c] = __ffma2_rn(c3, xa[3 % NJ], accA[c]);
-              accB[c] = __ffma2_rn(c3, xb[3 % NJ], accB[c]);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+              acc[r][c] = __ffma2_rn(make_float2(c01.x, c01.y), x[r][0], acc[r][c]);
+              if (NJ > 1) acc[r][c] = __ffma2_rn(make_float2(c01.z, c01.w), x[r][1 % NJ], acc[r][c]);
+              if (NJ > 2) acc[r][c] = __ffma2_rn(c2, x[r][2 % NJ], acc[r][c]);
+              if (NJ > 3) acc[r][c] = __ffma2_rn(c3, x[r][3 % NJ], acc[r][c]);
             }
           }
         }
         ip += a.CT;
       }
     }
-    // emit rows ra (and ra + 1): lanes hold columns lane and lane + 32
+    // emit: lanes hold columns lane and lane + 32 of each row
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-      const int wo = lane + 32 * half;
-      if (wo < a.Wo) {
-        float* outA = a.dst + ((static_cast<size_t>(n) * a.Ho + ho0 + ra) * a.Wo + wo) * a.Cout + g * a.Kg + cbase;
+    for (int r = 0; r < ROWS; r++) {
+      if (ho0 + ra + r >= ho_end) break;
 #pragma unroll
-        for (int c = 0; c < CPT; c += 4) {
-          float4 o = half ? make_float4(accA[c].y, accA[c + 1].y, accA[c + 2].y, accA[c + 3].y)
-                          : make_float4(accA[c].x, accA[c + 1].x, accA[c + 2].x, accA[c + 3].x);
-          if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          *reinterpret_cast<float4*>(outA + c) = o;
-        }
-        if (hasB) {
-          float* outB = outA + static_cast<size_t>(a.Wo) * a.Cout;
+      for (int half = 0; half < 2; half++) {
+        const int wo = lane + 32 * half;
+        if (wo < a.Wo) {
+          float* out = a.dst + ((static_cast<size_t>(n) * a.Ho + ho0 + ra + r) * a.Wo + wo) * a.Cout + g * a.Kg + cbase;
 #pragma unroll
           for (int c = 0; c < CPT; c += 4) {
-            float4 o = half ? make_float4(accB[c].y, accB[c + 1].y, accB[c + 2].y, accB[c + 3].y)
-                            : make_float4(accB[c].x, accB[c + 1].x, accB[c + 2].x, accB[c + 3].x);
+            float4 o = half ? make_float4(acc[r][c].y, acc[r][c + 1].y, acc[r][c + 2].y, acc[r][c + 3].y)
+                            : make_float4(acc[r][c].x, acc[r][c + 1].x, acc[r][c + 2].x, acc[r][c + 3].x);
             if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *reinterpret_cast<float4*>(outB + c) = o;
+            *reinterpret_cast<float4*>(out + c) = o;
           }
         }
       }
@@ -1119,7 +1109,7 @@ int LaunchOne(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
 
 namespace qcnn {
 
-constexpr size_t kMaxCand = 12;
+constexpr size_t kMaxCand = 18;
 
 // Chooses the tiling of a conv layer for batch size N.  Cost model in SM-cycles per CTA, times the number of
 // waves the whole batch needs on this GPU (so small batches trade LUT rebuilds for parallelism):
@@ -1251,25 +1241,30 @@ int PlanConv(qcnn_layer* L, int N) {
       for (int nct = 1; nct <= 2; nct++) {
         if (Kg % nct != 0 || (Kg / nct) % 16 != 0 || (Kg / nct) % CPT != 0) continue;
         const int CT = Kg / nct, cwarps = CT / CPT;
-        for (int R = 2; R <= L->Ho + 1; R += 2) {
-          for (int rgroups = 1; rgroups <= 4; rgroups++) {
+        const int Rs[5] = {2, 4, 6, 8, 14};
+        for (int ri = 0; ri < 5; ri++) {
+          const int R = Rs[ri];
+          if (R > L->Ho + 1) continue;
+          for (int rgroups = 1; rgroups <= 2; rgroups++)
+          for (int rowsPer = 2; rowsPer <= (CPT == 8 ? 4 : 2); rowsPer += 2) {
+            if (rgroups > R / rowsPer) continue;
             ConvPlan p;
             memset(&p, 0, sizeof(p));
             ConvArgs& a = p.a;
-            p.kernel = 4; p.CPT = CPT; p.J = 2;
+            p.kernel = 4; p.CPT = CPT; p.J = rowsPer;
             a.R = std::min(R, L->Ho + (L->Ho & 1)); a.nstrips = CeilDiv(L->Ho, a.R);
             a.CT = CT; a.nct = nct; a.cwarps = cwarps; a.pwarps = 1; a.rgroups = rgroups; a.ksplit = 1;
             a.PW = CeilDiv(L->Win + 2 * L->pad, L->stride);       // phase length
             a.PP = RoundUp(a.PW * L->stride, 4);                   // row pitch
             p.threads = 32 * cwarps * rgroups;
-            if (p.threads > 512 || p.threads < 128) continue;
+            if (p.threads > 384 || p.threads < 128) continue;
             const int rowsIn = (a.R - 1) * L->stride + L->ksz;
             p.smem = sizeof(float) * (static_cast<size_t>(rowsIn) * NJ * a.PP + 64 + 8 * static_cast<size_t>(L->K) +
                                       static_cast<size_t>(taps) * CT);
             if (p.smem > smemMax) continue;
-            const int pairs = a.R / 2;
+            const int pairs = CeilDiv(a.R, rowsPer);
             // issue slots: per (row pair, tap, channel) 2 loads + 2*NJ FFMA2, plus 4*NJ pixel loads per tap
-            const double perWarp = static_cast<double>(CeilDiv(pairs, rgroups)) * taps * (CPT * (2.0 + 2.0 * NJ) + 4.0 * NJ + CPT / 4.0);
+            const double perWarp = static_cast<double>(CeilDiv(pairs, rgroups)) * taps * (CPT * (2.0 + rowsPer * NJ) + 2.0 * rowsPer * NJ + CPT / 4.0);
             const double perCta = perWarp * cwarps * rgroups / 2.6 + rowsIn * NJ * a.PP * 0.5;
             const double ctas = static_cast<double>(G) * nct * a.nstrips * N;
             const double waves = std::ceil(ctas / L->ctx->sm_count);
@@ -1299,7 +1294,7 @@ int PlanConv(qcnn_layer* L, int N) {
     int perKernel[5] = {0, 0, 0, 0, 0};
     for (size_t i = 0; i < cands.size() && L->cands->size() < kMaxCand; i++) {
       ConvPlan c = cands[i].second;
-      if (pass == 0 && perKernel[c.kernel] >= 2) continue;
+      if (pass == 0 && perKernel[c.kernel] >= (c.kernel == 4 ? 8 : 2)) continue;
       ConvArgs& a = c.a;
       a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
       a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = G; a.Cg = Cg; a.Kg = Kg;
@@ -1309,7 +1304,7 @@ int PlanConv(qcnn_layer* L, int N) {
       bool dup = false;
       for (const ConvPlan& e : *L->cands)
         if (e.kernel == c.kernel && e.CPT == c.CPT && e.J == c.J && e.a.nct == c.a.nct && e.a.nstrips == c.a.nstrips &&
-            e.a.rgroups == c.a.rgroups) dup = true;
+            e.a.rgroups == c.a.rgroups && e.a.R == c.a.R && (e.kernel != 4 || e.J == c.J)) dup = true;
       if (dup) continue;
       L->cands->push_back(c);
       perKernel[c.kernel]++;
@@ -1330,10 +1325,10 @@ int PlanConv(qcnn_layer* L, int N) {
   return 0;
 }
 
-template <int CPT, int NJ>
+template <int CPT, int NJ, int ROWS>
 static int LaunchDirect(const ConvPlan& p, const ConvArgs& a, cudaStream_t st) {
   dim3 grid(a.G * a.nct * a.nstrips, a.N);
-  auto kern = conv_direct_kernel<CPT, NJ>;
+  auto kern = conv_direct_kernel<CPT, NJ, ROWS>;
   QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   kern<<<grid, p.threads, p.smem, st>>>(a);
   QCNN_CUDA(cudaGetLastError());
@@ -1346,8 +1341,10 @@ static int LaunchPlan(qcnn_layer* L, const ConvPlan& p, const float* src, int N,
   a.N = N; a.relu = relu; a.src_nchw = L->src_nchw;
   if (p.kernel == 4) {
     const int nj = std::min(a.Cg, a.d);
-    if (p.CPT == 16) return nj <= 3 ? LaunchDirect<16, 3>(p, a, st) : LaunchDirect<16, 4>(p, a, st);
-    return nj <= 3 ? LaunchDirect<8, 3>(p, a, st) : LaunchDirect<8, 4>(p, a, st);
+    // p.J carries the output rows per thread (2 or 4)
+    if (p.CPT == 16) return nj <= 3 ? LaunchDirect<16, 3, 2>(p, a, st) : LaunchDirect<16, 4, 2>(p, a, st);
+    if (p.J == 4) return nj <= 3 ? LaunchDirect<8, 3, 4>(p, a, st) : LaunchDirect<8, 4, 4>(p, a, st);
+    return nj <= 3 ? LaunchDirect<8, 3, 2>(p, a, st) : LaunchDirect<8, 4, 2>(p, a, st);
   }
   QCNN_CHECK(!(a.src_nchw && (p.kernel == 0 || p.kernel == 2)), "qcnn_conv_aprx_forward: NCHW source is only supported by the strided kernel");
   int rc = 1;

@@ -249,7 +249,8 @@ int Launch(const FcArgs& a, dim3 grid, cudaStream_t st) {
 }
 
 template <int K, bool PRE>
-int LaunchK(const FcArgs& a, int tn, dim3 grid, cudaStream_t st) {
+int LaunchK(const FcArgs& a, int tn, int cpt, dim3 grid, cudaStream_t st) {
+  if (cpt == 4 && tn == 8) return Launch<K, 4, 8, (K <= 32 ? 32 : (K <= 64 ? 16 : 8)), PRE>(a, grid, st);
   switch (tn) {
     case 1: return Launch<K, 16, 1, (K <= 64 ? 16 : 8), PRE>(a, grid, st);
     case 4: return Launch<K, 8, 4, (K <= 32 ? 32 : (K <= 64 ? 16 : 8)), PRE>(a, grid, st);
@@ -281,7 +282,8 @@ int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaS
   // batch tile: 1 (latency path, 16 channels/thread, 128-bit loads), 4 or 8 images per CTA
   int tn = L->opt_fc_tn ? L->opt_fc_tn : (N >= 8 ? 8 : (N >= 4 ? 4 : 1));
   if (tn != 1 && tn != 4) tn = 8;
-  const int cpt = (tn == 1) ? 16 : 8;
+  // narrow layers (fc8: 1000 outputs) take 4 channels per thread so that a 256-thread CTA is fully populated
+  const int cpt = (tn == 1) ? 16 : ((tn == 8 && L->DoutPad <= 1024) ? 4 : 8);
   const int pf = ChunkLen(L->K, tn);
   const int gx = CeilDiv(L->DoutPad, kFcThreads * cpt);
   const int gy = CeilDiv(N, tn);
@@ -312,11 +314,11 @@ int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaS
   int rc;
   const bool pre = L->kshift == 2;
   switch (L->K) {
-    case 16:  rc = pre ? LaunchK<16, true>(a, tn, grid, st) : LaunchK<16, false>(a, tn, grid, st); break;
-    case 32:  rc = pre ? LaunchK<32, true>(a, tn, grid, st) : LaunchK<32, false>(a, tn, grid, st); break;
-    case 64:  rc = pre ? LaunchK<64, true>(a, tn, grid, st) : LaunchK<64, false>(a, tn, grid, st); break;
-    case 128: rc = LaunchK<128, false>(a, tn, grid, st); break;
-    case 256: rc = LaunchK<256, false>(a, tn, grid, st); break;
+    case 16:  rc = pre ? LaunchK<16, true>(a, tn, cpt, grid, st) : LaunchK<16, false>(a, tn, cpt, grid, st); break;
+    case 32:  rc = pre ? LaunchK<32, true>(a, tn, cpt, grid, st) : LaunchK<32, false>(a, tn, cpt, grid, st); break;
+    case 64:  rc = pre ? LaunchK<64, true>(a, tn, cpt, grid, st) : LaunchK<64, false>(a, tn, cpt, grid, st); break;
+    case 128: rc = LaunchK<128, false>(a, tn, cpt, grid, st); break;
+    case 256: rc = LaunchK<256, false>(a, tn, cpt, grid, st); break;
     default:
       SetError("qcnn_fc_aprx_forward: unsupported codebook size K=%d (supported: 16, 32, 64, 128, 256)", L->K);
       return 1;

@@ -45,6 +45,27 @@ def kernels_table(rep, out_path, title):
             f.write(",".join(vals) + "\n")
 
 
+def traffic_json(rep, out_path):
+    """dram__bytes_read + dram__bytes_write per launch for the PQ / LRN kernels of ONE forward pass, in launch order."""
+    import json
+    rows = ncu_csv(rep, "raw")
+    hdr = rows[0]
+    order = ["conv1", "lrn1+pool1", "conv2", "lrn2+pool2", "conv3", "conv4", "conv5", "fc6", "fc7", "fc8"]
+    out, i = {}, 0
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if "reduce" in name or i >= len(order):
+            continue
+
+        def mb(col):
+            v = float(r[hdr.index(col)])
+            unit = rows[1][hdr.index(col)].lower()
+            return v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        out[order[i]] = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
+        i += 1
+    json.dump(out, open(out_path, "w"), indent=1)
+
+
 def stage_split(rep, out_path, title):
     """Per kernel: share of stall samples / instructions / shared-memory wavefronts between consecutive barriers
     (== the staging / LUT / gather stages of the conv kernels)."""
@@ -116,6 +137,7 @@ if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     kernels_table(rep, os.path.join(ROOT, "profiles", "%s_ncu_full_b256.csv" % tag),
                   "ncu --set full --clock-control none --import-source on; tools/profile_step.py --batch 256 (AlexNet PQ forward)")
+    traffic_json(rep, os.path.join(ROOT, "profiles", "traffic.json"))
     stage_split(rep, os.path.join(ROOT, "profiles", "%s_stage_split_b256.md" % tag),
                 "Where the time goes inside each kernel (stall samples between barriers), from the same capture")
     if launches and os.path.exists(launches):

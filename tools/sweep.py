@@ -1,0 +1,90 @@
+"""BASELINE.json configs[4]: per-layer synthetic sweep of the conv2..conv5 PQ kernels.
+subspaces per group S in {4, 8, 16} (d = Cg / S), codebook size K in {64, 128, 256}, batch N in {1, 256};
+reports time (CUDA events, median of reps), achieved GB/s on the algorithmic bytes of SURVEY.md 8(d) against the
+measured HBM peak, and lookups/s against the shared-memory gather bound.  Each N = 1 case is also checked against
+the CPU oracle (tests tolerance).
+    python tools/sweep.py [--reps 5] [--out profiles/r01_sweep.csv]
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+GEOM = {  # name: (Hi, Cin, Cout, k, pad, G)   SURVEY.md 8(d) config 5
+    "conv2": (27, 96, 256, 5, 2, 2),
+    "conv3": (13, 256, 384, 3, 1, 1),
+    "conv4": (13, 384, 384, 3, 1, 2),
+    "conv5": (13, 384, 256, 3, 1, 2),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_sweep.csv"))
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    import torch
+    q = importlib.import_module("quantized-cnn_b200")
+    from oracle import pyoracle as po      # checker only
+    ctx = q.Context(0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    gather_peak = 32.0 * ctx.sm_count * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    rows = ["layer,S_per_group,K,d,N,ms,alg_MB,alg_GBps,frac_hbm_peak,lookups_per_s,frac_smem_gather_bound,max_err_vs_oracle,kernel"]
+    for name, (Hi, Cin, Cout, k, pad, G) in GEOM.items():
+        Cg = Cin // G
+        for S in (4, 8, 16):
+            d = Cg // S
+            for K in (64, 128, 256):
+                seed = sum(map(ord, name)) * 1000 + S * 10 + K // 64
+                rng = np.random.RandomState(seed)
+                ctrd = (rng.randn(S, K, d) * 0.05).astype(np.float32)
+                asmt = rng.randint(0, K, size=(Cout, k, k, S)).astype(np.uint8)
+                bias = (rng.randn(Cout) * 0.1).astype(np.float32)
+                layer = q.ConvLayer(ctx, Cin, Hi, Hi, Cout, k, pad, 1, G, ctrd, asmt, bias)
+                for N in (1, 256):
+                    x = (np.abs(rng.randn(N, Hi, Hi, Cin)) * 20).astype(np.float32)
+                    xd = torch.from_numpy(x).cuda()
+                    y = layer.forward(xd)           # warm-up + tiling choice
+                    torch.cuda.synchronize()
+                    err = float("nan")
+                    if N == 1 and not args.no_check:
+                        ref = po.conv_aprx(x, po.conv(pad, k, Cout, G, 1), ctrd, asmt, bias)
+                        scale = np.maximum(np.maximum(1.0, np.abs(ref)), 0.1 * np.abs(ref).max())
+                        err = float((np.abs(y.cpu().numpy() - ref) / scale).max())
+                        assert err <= 1e-4, (name, S, K, err)
+                    ms = []
+                    for _ in range(args.reps):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        layer.forward(xd)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        ms.append(e0.elapsed_time(e1))
+                    t = float(np.median(ms))
+                    w = layer.work(N)
+                    desc = layer.describe(N).split(" ")[0]
+                    rows.append("%s,%d,%d,%d,%d,%.4f,%.2f,%.1f,%.4f,%.3e,%.4f,%.2e,%s" % (
+                        name, S, K, d, N, t, w["alg_bytes"] / 1e6, w["alg_bytes"] / (t * 1e-3) / 1e9,
+                        w["alg_bytes"] / (t * 1e-3) / 1e9 / hbm, w["lookups"] / (t * 1e-3),
+                        w["lookups"] / (t * 1e-3) / gather_peak, err, desc))
+                    print(rows[-1], flush=True)
+                layer.close()
+    with open(args.out, "w") as f:
+        f.write("# BASELINE.json configs[4] sweep; HBM peak %.1f GB/s (MEASURED_PEAKS.json), smem-gather bound %.3e lookups/s\n" % (hbm, gather_peak))
+        f.write("\n".join(rows) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -77,10 +77,17 @@ struct ConvArgs {
   int pwarps, cwarps, rgroups;
   int ksplit;           // LUT build: K is split over ksplit thread groups
   int relu;
+  // decode-at-use tensor-core kernel (conv_dec_tc.cu): flat padded grid over the whole batch
+  int IB;               // flat positions per image = (Hi + pad) * PW
+  int MT;               // 128-position M tiles per CTA
+  int NPOS;             // input positions staged per CTA = MT*128 + halo (multiple of 8)
+  int GT;               // taps per weight-tile stage
+  int NKC;              // 8-channel chunks per group
+  int tmemCols;         // TMEM allocation (power of two >= MT*CT)
 };
 
 struct ConvPlan {
-  int kernel;           // 0 = stride-1 flat kernel, 1 = rolling-row kernel
+  int kernel;           // 0 s1, 1 roll, 2 s1_tc, 3 roll_tc, 4 direct, 5 dec_tc (decode-at-use implicit GEMM on tcgen05)
   int CPT, J;
   int threads;
   size_t smem;
@@ -124,6 +131,9 @@ int PlanConv(qcnn_layer* L, int N);
 int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap);
 int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st);
 int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st);
+// conv_dec_tc.cu
+void PlanConvDec(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
+int LaunchConvDec(const ConvPlan& p, const ConvArgs& a, cudaStream_t st);
 
 int LaunchRelu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, cudaStream_t st);
 int LaunchLrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha, float beta,

@@ -1279,6 +1279,7 @@ int PlanConv(qcnn_layer* L, int N) {
   {
     const size_t before = cands.size();
     PlanConvDec(L, N, &cands);
+    PlanPqGemm(L, N, &cands);
     found = found || cands.size() > before;
   }
   QCNN_CHECK(found, "qcnn_conv_layer_create: no tiling fits (Cout/grp=%d must be a multiple of 16; K=%d must be a "
@@ -1288,7 +1289,7 @@ int PlanConv(qcnn_layer* L, int N) {
   std::stable_sort(cands.begin(), cands.end(), [](const std::pair<double, ConvPlan>& x, const std::pair<double, ConvPlan>& y) { return x.first < y.first; });
   if (!L->cands) L->cands = new std::vector<ConvPlan>();
   L->cands->clear();
-  // QCNN_FORCE_KERNEL=<0 s1 | 1 roll | 2 s1_tc | 3 roll_tc | 4 direct | 5 dec_tc> restricts the choice (tests / experiments)
+  // QCNN_FORCE_KERNEL=<0 s1 | 1 roll | 2 s1_tc | 3 roll_tc | 4 direct | 5 dec_tc | 6 pq_gemm_tc> restricts the choice (tests / experiments)
   const char* force = getenv("QCNN_FORCE_KERNEL");
   if (force) {
     std::vector<std::pair<double, ConvPlan>> kept;
@@ -1297,10 +1298,10 @@ int PlanConv(qcnn_layer* L, int N) {
   }
   // every kernel family that has a feasible tiling gets at least two seats among the candidates
   for (int pass = 0; pass < 2; pass++) {
-    int perKernel[6] = {0, 0, 0, 0, 0, 0};
+    int perKernel[7] = {0, 0, 0, 0, 0, 0, 0};
     for (size_t i = 0; i < cands.size() && L->cands->size() < kMaxCand; i++) {
       ConvPlan c = cands[i].second;
-      if (pass == 0 && perKernel[c.kernel] >= (c.kernel == 4 ? 8 : (c.kernel == 5 ? 6 : 2))) continue;
+      if (pass == 0 && perKernel[c.kernel] >= (c.kernel == 4 ? 8 : (c.kernel == 5 ? 4 : (c.kernel == 6 ? 6 : 2)))) continue;
       ConvArgs& a = c.a;
       a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
       a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = G; a.Cg = Cg; a.Kg = Kg;
@@ -1345,6 +1346,7 @@ static int LaunchPlan(qcnn_layer* L, const ConvPlan& p, const float* src, int N,
   ConvArgs a = p.a;
   a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
   a.N = N; a.relu = relu; a.src_nchw = L->src_nchw;
+  if (p.kernel == 6) return LaunchPqGemm(L, p, src, N, dst, relu, st);
   if (p.kernel == 5) return LaunchConvDec(p, a, st);
   if (p.kernel == 4) {
     const int nj = std::min(a.Cg, a.d);
@@ -1404,6 +1406,12 @@ int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
 int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
   if (int prc = PlanConv(L, N)) return prc;
   const ConvPlan& p = L->plan;
+  if (p.kernel == 6) {
+    snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM) mode=%d NT=%d GT=%d slots=%d smem=%zuB grid=%d NPOS=%d "
+             "chunks=%d ksteps/chunk=%d", p.g.mode, p.g.NT, p.g.GT, p.g.NSLOT, p.smem,
+             CeilDiv(N * p.g.IB, p.g.NT) * L->grp * p.g.nct, p.g.NPOS, p.g.nChunks, p.g.chunkCount[0]);
+    return 0;
+  }
   if (p.kernel == 5) {
     snprintf(buf, cap, "conv_dec_tc(tcgen05 decode-at-use GEMM) CT=%d MT=%d GT=%d threads=%d smem=%zuB grid=%d NPOS=%d "
              "chunks=%d tmemCols=%d", p.a.CT, p.a.MT, p.a.GT, p.threads, p.smem,

@@ -35,6 +35,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWorkers = 224;   // decode threads (warps 0..6); thread kWorkers issues the MMAs
 
 __device__ __forceinline__ uint32_t SmemU32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -178,40 +179,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dec_tc_kernel(const ConvArgs
     }
   };
   // ---- weight tiles of taps [t0, t0+nt): gather the codeword halves the assignment indices name ----
+  // warp 7 only issues MMAs; warps 0..6 decode, so the issue of stage t overlaps the decode of stage t+1
   auto decodeStage = [&](int kc, int t0, int nt, int buf) {
+    if (tid >= kWorkers) return;
     const int ab = kc & 1;
-    const uint8_t* idb = idN + ab * 2 * taps * CT;
     const float4* cHi = cbs + (ab * 2 + 0) * 2 * K;
     const float4* cLo = cbs + (ab * 2 + 1) * 2 * K;
     const int per = 2 * CT;
-    for (int e = tid; e < nt * per; e += kThreads) {
-      const int tapi = e / per, r = e - tapi * per;
-      const int half = r >= CT ? 1 : 0, c = r - half * CT;
-      const int idx = idb[(half * taps + t0 + tapi) * CT + c];
+    for (int tapi = 0; tapi < nt; tapi++) {
+      const uint8_t* idb = idN + ab * 2 * taps * CT + (t0 + tapi) * CT;
       float4* Bt = Bbuf + (buf * GT + tapi) * 4 * CT;
-      const int o = (c >> 3) * 16 + half * 8 + (c & 7);
-      Bt[o] = cHi[half * K + idx];
-      Bt[2 * CT + o] = cLo[half * K + idx];
+      for (int r = tid; r < per; r += kWorkers) {
+        const int half = r >= CT ? 1 : 0, c = r - half * CT;
+        const int idx = idb[half * taps * CT + c];
+        const int o = (c >> 3) * 16 + half * 8 + (c & 7);
+        Bt[o] = cHi[half * K + idx];
+        Bt[2 * CT + o] = cLo[half * K + idx];
+      }
     }
   };
+  // descriptors advance by (bytes >> 4) in their low word: A by the tap shift / 128 positions per M tile, B per tap
   auto issueStage = [&](int kc, int t0, int nt, int buf) {  // one thread
     const int ab = kc & 1;
-    const uint32_t aHi = SmemU32(Abuf + (ab * 2 + 0) * 2 * NPOS), aLo = SmemU32(Abuf + (ab * 2 + 1) * 2 * NPOS);
     const uint32_t lboA = static_cast<uint32_t>(NPOS) * 16u;
+    const uint64_t dAh0 = Desc(SmemU32(Abuf + (ab * 2 + 0) * 2 * NPOS), lboA, 128);
+    const uint64_t dAl0 = Desc(SmemU32(Abuf + (ab * 2 + 1) * 2 * NPOS), lboA, 128);
+    uint64_t dBh = Desc(SmemU32(Bbuf + buf * GT * 4 * CT), 128, 256);
+    const uint64_t bLo = static_cast<uint64_t>(2 * CT), bTap = static_cast<uint64_t>(4 * CT);
+    int kh = t0 / a.ksz, kw = t0 - kh * a.ksz;
+    uint32_t acc = (kc | t0) != 0 ? 1u : 0u;
     for (int tapi = 0; tapi < nt; tapi++) {
-      const int tap = t0 + tapi;
-      const int kh = tap / a.ksz, kw = tap - kh * a.ksz;
-      const uint32_t shift = static_cast<uint32_t>(kh * a.PW + kw) * 16u;
-      const uint32_t bHi = SmemU32(Bbuf + (buf * GT + tapi) * 4 * CT), bLo = bHi + static_cast<uint32_t>(CT) * 32u;
-      const uint64_t dBh = Desc(bHi, 128, 256), dBl = Desc(bLo, 128, 256);
+      const uint64_t shift = static_cast<uint64_t>(kh * a.PW + kw);
+      uint64_t dAh = dAh0 + shift, dAl = dAl0 + shift;
+      uint32_t d = tmemD;
       for (int m = 0; m < MT; m++) {
-        const uint32_t ao = static_cast<uint32_t>(m) * 2048u + shift;
-        const uint64_t dAh = Desc(aHi + ao, lboA, 128), dAl = Desc(aLo + ao, lboA, 128);
-        const uint32_t d = tmemD + static_cast<uint32_t>(m * CT);
-        UmmaTf32(d, dAh, dBh, idesc, (kc | tap) != 0 ? 1u : 0u);
-        UmmaTf32(d, dAh, dBl, idesc, 1u);
+        UmmaTf32(d, dAh, dBh, idesc, acc);
+        UmmaTf32(d, dAh, dBh + bLo, idesc, 1u);
         UmmaTf32(d, dAl, dBh, idesc, 1u);
+        dAh += 128; dAl += 128; d += static_cast<uint32_t>(CT);
       }
+      acc = 1u;
+      dBh += bTap;
+      if (++kw == a.ksz) { kw = 0; kh++; }
     }
   };
 
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dec_tc_kernel(const ConvArgs
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
       if (last && kc + 2 < NKC) { fetchRaw(kc + 2); CpAsyncCommit(); }
-      if (tid == 0) {
+      if (tid == kWorkers) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         issueStage(kc, t0, nt, buf);
         UmmaCommit(mbar + buf);

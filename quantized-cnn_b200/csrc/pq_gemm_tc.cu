@@ -1,0 +1,428 @@
+// PQ layers as decode-at-use GEMMs on the 5th-generation tensor cores, weights decoded straight into tensor memory.
+//
+//     dst[q][c] = bias[c] + sum_{k-steps} sum_{j<8}  W_kstep[c][j] * X_kstep[q][j]
+//
+// One k-step is 8 input values of every position q (two 4-float halves); W_kstep[c][half] is the 4-float piece of the
+// codeword that channel c's uint8 assignment index names for that half -- the same codebook + index arrays the LUT /
+// gather kernels use (reference CaffeEva::CalcFeatMap_ConvAprx / _FCntAprx + GetInPdMat, src/CaffeEva.cc:760-868,
+// 968-1025, 1261-1296, evaluated as x . (decoded w) instead of gather(LUT(x)); same sums, different association).
+//
+// Roles inside a CTA (256 threads, warp-specialised, mbarrier pipelines, no CTA-wide barrier in the main loop):
+//   warps 0-3  decoders: thread = output channel (= TMEM lane).  Per k-step: index byte(s) -> codeword half(s) from the
+//              staged codebook slice -> hi (tf32) / lo (exact remainder) in registers -> tcgen05.st into the A ring in
+//              TMEM (16 columns per k-step: 8 hi + 8 lo).  Decoded weights never touch shared memory.
+//   warp 4     one thread issues tcgen05.mma (kind::tf32, M = 128 channels, N = NT positions, K = 8) with A in TMEM and
+//              B = the position planes in shared memory; three MMAs per k-step (3xTF32: Ah*Bh + Ah*Bl + Al*Bh).
+//   warps 5-7  stagers: cp.async the next chunk's positions (raw) + codebook slices + index rows, split the positions
+//              into hi/lo planes (K-major, SWIZZLE_NONE core matrices: 8 positions x 16 B, SBO = 128 B, LBO = distance
+//              between the two halves), double-buffered against the MMAs of the current chunk.
+//   all warps  epilogue: TMEM (lane = channel, column = position) -> + bias, ReLU -> NHWC stores (a warp writes 32
+//              consecutive channels of one position: 128 B).
+// Shared-memory traffic per k-step is the B operand only (NT x 32 B per MMA = 64 B/clk at the MMA floor) plus the
+// decoders' index / codeword reads, so the tensor pipe, not shared memory, is the limit (the first version of this
+// kernel kept the decoded weights in shared memory and was bound by operand fetch: profiles/r01_dec_tc_v1.md).
+//
+// Layer geometries are expressed as a table of k-steps (KStep: B start / half distance inside the staged planes, index
+// row and codebook slot of either half), so one main loop serves
+//   mode 0  stride-1 convolutions: all images form one flat padded grid (image block = (Hi+pad) rows of pitch Wi+pad;
+//           the leading pad rows / columns are zero and double as the previous row's / image's trailing padding), a tap
+//           is a start-address shift of the B descriptor, a chunk is 8 input channels x all taps;
+//   mode 1  strided convolutions with <= 4 input channels (conv1: 11x11 / 4): input de-interleaved into stride x stride
+//           phase planes so that a tap again is a shift; a k-step pairs two taps (4 floats each: channels + zero pad);
+//           a chunk is one phase row;
+//   mode 2  fully-connected layers: position = image, a chunk is a run of k-steps over consecutive input features.
+#include "qcnn_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kDecoders = 128;   // warps 0-3
+constexpr int kIssuer = 128;     // first lane of warp 4
+constexpr int kStagers = 96;     // warps 5-7
+constexpr int kStager0 = 160;
+constexpr int kMaxSlots = 5;
+
+__device__ __forceinline__ uint32_t SmemU32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void CpAsync16(void* smemDst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0: nothing is read, the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(SmemU32(smemDst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void CpAsync4(void* smemDst, const void* gsrc, bool valid) {
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(SmemU32(smemDst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void CpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void MbarInit(uint64_t* mbar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemU32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void MbarArrive(uint64_t* mbar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(SmemU32(mbar)) : "memory");
+}
+// bounded spin: a protocol error traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void MbarWait(uint64_t* mbar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; spins++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(SmemU32(mbar)), "r"(parity) : "memory");
+    if (spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void UmmaCommit(uint64_t* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemU32(mbar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void UmmaTf32Ts(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmemD), "r"(tmemA), "l"(descB),
+               "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void SplitTf32x4(const float4 v, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+}
+
+struct SmemMap {  // byte offsets inside the dynamic shared memory
+  int planes, raw, cbs, ids, tab, posoff, outoff, bias, bars, tmem, total;
+};
+__host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
+  SmemMap m;
+  int o = 0;
+  m.planes = o; o += 2 * 2 * a.planeF4 * 16;            // [buf][hi,lo][planeF4]
+  m.raw = o;    o += a.planeF4 * 16;                    // cp.async target of the positions
+  m.cbs = o;    o += 2 * a.cbSlots * a.K * 16;          // [buf][slot][K] codeword halves (raw fp32)
+  m.ids = o;    o += 2 * a.idRows * 128;                // [buf][row][128 channels] assignment indices
+  m.tab = o;    o += a.ntab * 16;
+  m.posoff = o; o += a.planeF4 * 4;                     // source element offset of every staged float4 (-1: zero)
+  m.outoff = o; o += 256 * 4;                           // destination element offset of every position (-1: none)
+  m.bias = o;   o += 128 * 4;
+  m.bars = o;   o += 8 * (2 * kMaxSlots + 7);
+  m.tmem = o;   o += 16;
+  m.total = o;
+  return m;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemMap sm = MapSmem(a);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = a.K, NT = a.NT, GT = a.GT, NSLOT = a.NSLOT, nChunks = a.nChunks;
+
+  float4* planes = reinterpret_cast<float4*>(smem + sm.planes);
+  float4* raw = reinterpret_cast<float4*>(smem + sm.raw);
+  float4* cbs = reinterpret_cast<float4*>(smem + sm.cbs);
+  uint8_t* ids = smem + sm.ids;
+  KStep* tabS = reinterpret_cast<KStep*>(smem + sm.tab);
+  int* posoff = reinterpret_cast<int*>(smem + sm.posoff);
+  int* outoff = reinterpret_cast<int*>(smem + sm.outoff);
+  float* biasS = reinterpret_cast<float*>(smem + sm.bias);
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + sm.bars);   // [kMaxSlots] decoders -> issuer
+  uint64_t* emptyA = fullA + kMaxSlots;                            // [kMaxSlots] MMAs retired -> decoders
+  uint64_t* fullBC = emptyA + kMaxSlots;                           // [2] stagers -> issuer + decoders
+  uint64_t* emptyB = fullBC + 2;                                   // [2] chunk's MMAs retired -> stagers
+  uint64_t* emptyC = emptyB + 2;                                   // [2] decoders done with the chunk -> stagers
+  uint64_t* doneBar = emptyC + 2;
+  uint32_t* tmemBase = reinterpret_cast<uint32_t*>(smem + sm.tmem);
+
+  int b = blockIdx.x;
+  const int gc = b % (a.G * a.nct);
+  const int tile = b / (a.G * a.nct);
+  const int ct = gc % a.nct, g = gc / a.nct;
+  const int ch0 = ct * 128;                            // first channel of the tile inside the group
+  const int CTv = min(128, a.Kg - ch0);                // valid channels
+  const int Q0 = tile * NT;                            // first flat position
+  const int i0 = Q0 / a.IB;                            // first image touched
+  const float* srcBase = a.src + static_cast<size_t>(i0) * a.srcImg;
+  float* dstBase = a.dst + static_cast<size_t>(i0) * a.dstImg + g * a.Kg + ch0;
+
+  // ---- set-up (all threads) ----
+  for (int e = tid; e < a.ntab; e += kThreads) tabS[e] = a.tab[e];
+  for (int p = tid; p < a.planeF4; p += kThreads) {
+    int off = -1;
+    if (a.mode == 0) {
+      // float4 p: half = p / NPOS, position = p % NPOS; the half only selects the channel offset (added per chunk)
+      const int pos = p % a.NPOS;
+      const int F = Q0 + pos;
+      const int i = F / a.IB, rem = F - i * a.IB;
+      const int r = rem / a.PW, c = rem - r * a.PW;
+      if (i < a.N && r >= a.pad && c >= a.pad) off = (((i - i0) * a.Hi + (r - a.pad)) * a.Wi + (c - a.pad)) * a.Cin;
+    }
+    posoff[p] = off;
+  }
+  for (int p = tid; p < 256; p += kThreads) {
+    int off = -1;
+    if (p < NT) {
+      const int Q = Q0 + p;
+      const int i = Q / a.IB, rem = Q - i * a.IB;
+      const int ho = rem / a.PW, wo = rem - ho * a.PW;
+      if (i < a.N && ho < a.Ho && wo < a.Wo) off = (((i - i0) * a.Ho + ho) * a.Wo + wo) * a.Cout;
+    }
+    outoff[p] = off;
+  }
+  for (int c = tid; c < 128; c += kThreads) biasS[c] = c < CTv ? __ldg(a.bias + g * a.Kg + ch0 + c) : 0.0f;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmemBase)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kMaxSlots; i++) { MbarInit(fullA + i, kDecoders); MbarInit(emptyA + i, 1); }
+    for (int i = 0; i < 2; i++) { MbarInit(fullBC + i, kStagers); MbarInit(emptyB + i, 1); MbarInit(emptyC + i, kDecoders); }
+    MbarInit(doneBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmemD = *tmemBase;          // D: columns [0, NT)
+  const uint32_t tmemA = tmemD + 256;        // A ring: columns [256, 256 + NSLOT*GT*16)
+
+  if (warp >= 5) {
+    // =========================== stagers ===========================
+    const int st = tid - kStager0;
+    for (int kc = 0; kc < nChunks; kc++) {
+      const int buf = kc & 1;
+      if (kc >= 2) {
+        const uint32_t par = ((kc >> 1) - 1) & 1;
+        MbarWait(emptyB + buf, par);
+        MbarWait(emptyC + buf, par);
+      }
+      if (a.mode == 0) {
+        // positions: float4 p = (half, pos): channels [kc*8 + half*4, +4) of the group
+        for (int p = st; p < a.planeF4; p += kStagers) {
+          const int off = posoff[p];
+          const int ch = kc * 8 + (p >= a.NPOS ? 4 : 0);
+          const bool ok = off >= 0 && ch < a.Cg;
+          CpAsync16(raw + p, srcBase + g * a.Cg + (ok ? off + ch : 0), ok);
+        }
+        // codebook slices: slot = half; indices: rows [half][tap]
+        const int taps = a.ksz * a.ksz;
+        for (int e = st; e < 2 * K; e += kStagers) {
+          const int half = e >= K ? 1 : 0, k = e - half * K;
+          const int ch = kc * 8 + half * 4;
+          const bool ok = ch < a.Cg;
+          const int s = ok ? ch / a.d : 0, j0 = ok ? ch - s * a.d : 0;
+          CpAsync16(cbs + (buf * a.cbSlots + half) * K + k, a.ctrd + (static_cast<size_t>(s) * K + k) * a.d + j0, ok);
+        }
+        const int gran = CTv >> 4;   // 16-byte granules of valid channels per row
+        for (int e = st; e < 2 * taps * gran; e += kStagers) {
+          const int row = e / gran, q = e - row * gran;
+          const int half = row >= taps ? 1 : 0, tap = row - half * taps;
+          const int ch = kc * 8 + half * 4;
+          const int s = ch < a.Cg ? ch / a.d : 0;
+          const uint8_t* gsrc = a.asmt + (static_cast<size_t>(g * a.S + s) * taps + tap) * a.KgPad + ch0 + (q << 4);
+          CpAsync16(ids + (buf * a.idRows + row) * 128 + (q << 4), gsrc, true);
+        }
+      }
+      CpAsyncCommit();
+      CpAsyncWaitAll();
+      asm volatile("bar.sync 1, 96;" ::: "memory");     // every stager's raw positions have landed
+      float4* pHi = planes + (buf * 2 + 0) * a.planeF4;
+      float4* pLo = planes + (buf * 2 + 1) * a.planeF4;
+      for (int p = st; p < a.planeF4; p += kStagers) {
+        float4 hi, lo;
+        SplitTf32x4(raw[p], hi, lo);
+        pHi[p] = hi;
+        pLo[p] = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // planes are read by the tensor core
+      MbarArrive(fullBC + buf);
+      asm volatile("bar.sync 1, 96;" ::: "memory");     // raw may be overwritten
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer ===========================
+    if (tid == kIssuer) {
+      // instruction descriptor: D = F32, A = B = TF32, K-major, N = NT, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) | (8u << 24);
+      const uint64_t descFixed = (static_cast<uint64_t>(8) << 32) | (static_cast<uint64_t>(1) << 46);  // SBO = 128 B
+      int t = 0;
+      uint32_t acc = 0;
+      for (int kc = 0; kc < nChunks; kc++) {
+        const int buf = kc & 1;
+        MbarWait(fullBC + buf, (kc >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dHi = descFixed | ((SmemU32(planes + (buf * 2 + 0) * a.planeF4) >> 4) & 0x3FFFu);
+        const uint64_t dLo = descFixed | ((SmemU32(planes + (buf * 2 + 1) * a.planeF4) >> 4) & 0x3FFFu);
+        const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0], ne = a.chunkCount[a.mode == 1 ? kc : 0];
+        for (int s0 = 0; s0 < ne; s0 += GT, t++) {
+          const int slot = t % NSLOT;
+          MbarWait(fullA + slot, (t / NSLOT) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int n = min(GT, ne - s0);
+          for (int i = 0; i < n; i++) {
+            const KStep ks = tabS[e0 + s0 + i];
+            const uint64_t off = static_cast<uint64_t>(static_cast<uint32_t>(ks.bStart)) |
+                                 (static_cast<uint64_t>(static_cast<uint32_t>(ks.lbo)) << 16);
+            const uint32_t aHi = tmemA + static_cast<uint32_t>((slot * GT + i) * 16), aLo = aHi + 8;
+            UmmaTf32Ts(tmemD, aHi, dHi + off, idesc, acc);
+            UmmaTf32Ts(tmemD, aHi, dLo + off, idesc, 1u);
+            UmmaTf32Ts(tmemD, aLo, dHi + off, idesc, 1u);
+            acc = 1u;
+          }
+          UmmaCommit(emptyA + slot);
+        }
+        UmmaCommit(emptyB + buf);
+      }
+      UmmaCommit(doneBar);
+    }
+  } else {
+    // =========================== decoders ===========================
+    const int c = tid;                              // channel row = TMEM lane
+    const int cc = min(c, CTv - 1);                 // rows beyond the valid channels decode a copy (never stored)
+    const uint32_t laneBase = static_cast<uint32_t>(warp * 32) << 16;
+    int t = 0;
+    for (int kc = 0; kc < nChunks; kc++) {
+      const int buf = kc & 1;
+      MbarWait(fullBC + buf, (kc >> 1) & 1);
+      const uint8_t* idb = ids + buf * a.idRows * 128 + cc;
+      const float4* cb = cbs + buf * a.cbSlots * K;
+      const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0], ne = a.chunkCount[a.mode == 1 ? kc : 0];
+      for (int s0 = 0; s0 < ne; s0 += GT, t++) {
+        const int slot = t % NSLOT;
+        if (t >= NSLOT) {
+          MbarWait(emptyA + slot, ((t / NSLOT) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int n = min(GT, ne - s0);
+        for (int i = 0; i < n; i++) {
+          const KStep ks = tabS[e0 + s0 + i];
+          const int i0x = idb[ks.idx0 * 128];
+          const int i1x = idb[ks.idx1 * 128];
+          const float4 w0 = cb[ks.cb0 * K + i0x];
+          const float4 w1 = cb[ks.cb1 * K + i1x];
+          float4 h0, l0, h1, l1;
+          SplitTf32x4(w0, h0, l0);
+          SplitTf32x4(w1, h1, l1);
+          const uint32_t taddr = tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                       "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                       :: "r"(taddr),
+                          "r"(__float_as_uint(h0.x)), "r"(__float_as_uint(h0.y)), "r"(__float_as_uint(h0.z)), "r"(__float_as_uint(h0.w)),
+                          "r"(__float_as_uint(h1.x)), "r"(__float_as_uint(h1.y)), "r"(__float_as_uint(h1.z)), "r"(__float_as_uint(h1.w)),
+                          "r"(__float_as_uint(l0.x)), "r"(__float_as_uint(l0.y)), "r"(__float_as_uint(l0.z)), "r"(__float_as_uint(l0.w)),
+                          "r"(__float_as_uint(l1.x)), "r"(__float_as_uint(l1.y)), "r"(__float_as_uint(l1.z)), "r"(__float_as_uint(l1.w))
+                       : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        MbarArrive(fullA + slot);
+      }
+      MbarArrive(emptyC + buf);
+    }
+  }
+
+  // ---- epilogue: TMEM (lane = channel, column = position) -> + bias, ReLU -> NHWC global ----
+  MbarWait(doneBar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const int q = warp & 3, hsel = warp >> 2;
+    const int c = q * 32 + lane;
+    const bool chOk = c < CTv;
+    const float bv = biasS[c];
+    const int nblk = NT >> 4;   // 16-position blocks
+    for (int blk = hsel; blk < nblk; blk += 2) {
+      uint32_t r[16];
+      const uint32_t taddr = tmemD + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(blk * 16);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                   "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                     "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                   : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int off = outoff[blk * 16 + j];
+        if (off >= 0 && chOk) {
+          float v = __uint_as_float(r[j]) + bv;
+          if (a.relu) v = fmaxf(v, 0.0f);
+          dstBase[off + c] = v;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "r"(512) : "memory");
+}
+
+}  // namespace
+
+namespace qcnn {
+
+// Candidate tilings for batch N (cost in SM-cycles, comparable with PlanConv's model): 3 MMAs of NT/2 clk per k-step.
+// env QCNN_NO_DECTC=1 removes the family (the LUT + gather kernels remain).
+void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands) {
+  if (getenv("QCNN_NO_DECTC") != nullptr) return;
+  const int G = L->grp, Cg = L->Cin / G, Kg = L->Cout / G, taps = L->ksz * L->ksz;
+  if (L->stride != 1 || L->src_nchw) return;
+  if (L->d % 4 != 0 || Cg % 4 != 0 || L->Cin % 4 != 0 || L->S * L->d < Cg) return;
+  if (L->K < 1 || L->K > 256 || Kg % 16 != 0 || taps > kMaxKSteps) return;
+  const int PW = L->Win + L->pad, IB = (L->Hin + L->pad) * PW;
+  if (L->Ho > L->Hin + L->pad || L->Wo > PW) return;
+  if (static_cast<double>(N) * IB > 2.0e9) return;
+  const size_t smemMax = L->ctx->smem_optin ? L->ctx->smem_optin : 227 * 1024;
+  const int nts[3] = {256, 128, 64};
+  for (int ni = 0; ni < 3; ni++) {
+    const int NT = nts[ni];
+    const int gts[3] = {4, 5, 8};
+    for (int gi = 0; gi < 3; gi++) {
+      const int GT = gts[gi];
+      ConvPlan p;
+      memset(&p, 0, sizeof(p));
+      p.kernel = 6; p.CPT = NT; p.J = GT; p.threads = kThreads;
+      GemmArgs& ga = p.g;
+      ga.mode = 0;
+      ga.PW = PW; ga.IB = IB; ga.NT = NT; ga.GT = GT; ga.NSLOT = std::min(kMaxSlots, 16 / GT);
+      ga.NPOS = RoundUp(NT + (L->ksz - 1) * (PW + 1), 8);
+      if (ga.NPOS > 16000) continue;
+      ga.planeF4 = 2 * ga.NPOS;
+      ga.cbSlots = 2; ga.idRows = 2 * taps;
+      ga.nChunks = CeilDiv(Cg, 8);
+      ga.ntab = taps;
+      ga.chunkFirst[0] = 0; ga.chunkCount[0] = taps;
+      for (int t = 0; t < taps; t++) {
+        KStep& ks = ga.tab[t];
+        ks.bStart = (t / L->ksz) * PW + (t % L->ksz);
+        ks.lbo = ga.NPOS;
+        ks.idx0 = static_cast<short>(t); ks.idx1 = static_cast<short>(taps + t);
+        ks.cb0 = 0; ks.cb1 = 1;
+      }
+      ga.K = L->K;
+      ga.nct = CeilDiv(Kg, 128);
+      p.smem = static_cast<size_t>(MapSmem(ga).total);
+      if (p.smem > smemMax) continue;
+      p.a.CT = 128; p.a.nct = ga.nct; p.a.R = NT; p.a.nstrips = GT; p.a.rgroups = 1;   // (candidate de-duplication keys)
+      const double ksteps = static_cast<double>(ga.nChunks) * taps;
+      const double perCta = ksteps * 3.0 * (NT / 2.0) * 1.1 + 120.0 * ksteps / GT + 4000.0 + NT * 24.0;
+      const double ctas = static_cast<double>(CeilDiv(N * IB, NT)) * G * ga.nct;
+      const double waves = std::ceil(ctas / L->ctx->sm_count);
+      cands->emplace_back(perCta * waves, p);
+    }
+  }
+}
+
+int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st) {
+  GemmArgs a = p.g;
+  a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
+  a.N = N; a.relu = relu;
+  a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
+  a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = L->grp; a.Cg = L->Cin / L->grp; a.Kg = L->Cout / L->grp;
+  a.KgPad = RoundUp(a.Kg, 16); a.S = L->S; a.K = L->K; a.d = L->d;
+  a.srcImg = static_cast<long long>(a.Hi) * a.Wi * a.Cin;
+  a.dstImg = static_cast<long long>(a.Ho) * a.Wo * a.Cout;
+  const long long blocks = static_cast<long long>(CeilDiv(N * a.IB, a.NT)) * a.G * a.nct;
+  QCNN_CHECK(blocks <= 2147483647LL, "qcnn_conv_aprx_forward: batch too large for the tensor-core tiling");
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  pq_gemm_tc_kernel<<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
+  QCNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace qcnn

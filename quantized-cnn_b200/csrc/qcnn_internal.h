@@ -86,12 +86,44 @@ struct ConvArgs {
   int tmemCols;         // TMEM allocation (power of two >= MT*CT)
 };
 
+// ---- decode-at-use tensor-core GEMM (pq_gemm_tc.cu) ----
+constexpr int kMaxKSteps = 96;
+struct KStep {           // one K = 8 step of the GEMM: two 4-float halves
+  int bStart;            // B operand: first float4 of half 0 inside the staged planes (position 0 of the tile)
+  int lbo;               // distance (in float4) from half 0 to half 1
+  short idx0, idx1;      // assignment-index row of either half inside the chunk's staged rows
+  short cb0, cb1;        // codebook slot of either half inside the chunk's staged slices
+};
+struct GemmArgs {
+  const float* src;
+  float* dst;
+  const float* ctrd;
+  const uint8_t* asmt;
+  const float* bias;
+  long long srcImg, dstImg;   // elements per source / destination image
+  int N, Hi, Wi, Cin, Ho, Wo, Cout, ksz, pad, stride, G, Cg, Kg, KgPad, S, K, d;
+  int mode;                   // 0 stride-1 conv, 1 strided conv on phase planes, 2 fully connected
+  int PW, IB;                 // flat grid: row pitch / positions per image
+  int NT;                     // positions per CTA = MMA N (multiple of 16, <= 256)
+  int NPOS;                   // staged positions per plane (NT + halo)
+  int planeF4;                // float4 per staged plane set (one of hi / lo, one buffer)
+  int cbSlots, idRows;        // codebook slices / index rows staged per chunk
+  int nChunks;
+  int GT, NSLOT;              // k-steps per stage, stages in the TMEM weight ring
+  int nct;                    // 128-channel tiles per group
+  int relu;
+  int ntab;
+  int chunkFirst[8], chunkCount[8];   // k-step table range of a chunk (mode 1: per phase row; else entry 0)
+  KStep tab[kMaxKSteps];
+};
+
 struct ConvPlan {
-  int kernel;           // 0 s1, 1 roll, 2 s1_tc, 3 roll_tc, 4 direct, 5 dec_tc (decode-at-use implicit GEMM on tcgen05)
+  int kernel;           // 0 s1, 1 roll, 2 s1_tc, 3 roll_tc, 4 direct, 5 dec_tc, 6 pq_gemm_tc (decode-at-use GEMMs on tcgen05)
   int CPT, J;
   int threads;
   size_t smem;
   ConvArgs a;           // geometry + tiling (pointers/N filled at launch)
+  GemmArgs g;           // kernel 6 (pq_gemm_tc)
 };
 
 struct qcnn_layer {
@@ -134,6 +166,9 @@ int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaS
 // conv_dec_tc.cu
 void PlanConvDec(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
 int LaunchConvDec(const ConvPlan& p, const ConvArgs& a, cudaStream_t st);
+// pq_gemm_tc.cu
+void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
+int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st);
 
 int LaunchRelu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, cudaStream_t st);
 int LaunchLrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha, float beta,

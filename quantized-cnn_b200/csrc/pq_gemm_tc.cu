@@ -37,6 +37,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 
 namespace {
 
@@ -46,6 +47,7 @@ constexpr int kIssuer = 128;     // first lane of warp 4
 constexpr int kStagers = 96;     // warps 5-7
 constexpr int kStager0 = 160;
 constexpr int kMaxSlots = 5;
+constexpr int kCbBufs = 3;      // codebook / index buffers: the decoders run ahead of the position planes
 
 __device__ __forceinline__ uint32_t SmemU32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void CpAsync16(void* smemDst, const void* gsrc, bool valid) {
@@ -98,13 +100,13 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   int o = 0;
   m.planes = o; o += 2 * 2 * a.planeF4 * 16;            // [buf][hi,lo][planeF4]
   m.raw = o;    o += a.planeF4 * 16;                    // cp.async target of the positions
-  m.cbs = o;    o += 2 * a.cbSlots * a.K * 16;          // [buf][slot][K] codeword halves (raw fp32)
-  m.ids = o;    o += 2 * a.idRows * 128;                // [buf][row][128 channels] assignment indices
+  m.cbs = o;    o += kCbBufs * a.cbSlots * a.K * 16;    // [cbuf][slot][K] codeword halves (raw fp32)
+  m.ids = o;    o += kCbBufs * a.idRows * 128;          // [cbuf][row][128 channels] assignment indices
   m.tab = o;    o += a.ntab * 16;
   m.posoff = o; o += a.planeF4 * 4;                     // source element offset of every staged float4 (-1: zero)
   m.outoff = o; o += 256 * 4;                           // destination element offset of every position (-1: none)
   m.bias = o;   o += 128 * 4;
-  m.bars = o;   o += 8 * (2 * kMaxSlots + 7);
+  m.bars = o;   o += 8 * (2 * kMaxSlots + 2 * kCbBufs + 5);
   m.tmem = o;   o += 16;
   m.total = o;
   return m;
@@ -126,10 +128,11 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   float* biasS = reinterpret_cast<float*>(smem + sm.bias);
   uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + sm.bars);   // [kMaxSlots] decoders -> issuer
   uint64_t* emptyA = fullA + kMaxSlots;                            // [kMaxSlots] MMAs retired -> decoders
-  uint64_t* fullBC = emptyA + kMaxSlots;                           // [2] stagers -> issuer + decoders
-  uint64_t* emptyB = fullBC + 2;                                   // [2] chunk's MMAs retired -> stagers
-  uint64_t* emptyC = emptyB + 2;                                   // [2] decoders done with the chunk -> stagers
-  uint64_t* doneBar = emptyC + 2;
+  uint64_t* fullB = emptyA + kMaxSlots;                            // [2] position planes: stagers -> issuer
+  uint64_t* emptyB = fullB + 2;                                    // [2] chunk's MMAs retired -> stagers
+  uint64_t* fullC = emptyB + 2;                                    // [kCbBufs] codebook + indices: stagers -> decoders
+  uint64_t* emptyC = fullC + kCbBufs;                              // [kCbBufs] decoders done with the chunk -> stagers
+  uint64_t* doneBar = emptyC + kCbBufs;
   uint32_t* tmemBase = reinterpret_cast<uint32_t*>(smem + sm.tmem);
 
   int b = blockIdx.x;
@@ -174,7 +177,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   }
   if (tid == 0) {
     for (int i = 0; i < kMaxSlots; i++) { MbarInit(fullA + i, kDecoders); MbarInit(emptyA + i, 1); }
-    for (int i = 0; i < 2; i++) { MbarInit(fullBC + i, kStagers); MbarInit(emptyB + i, 1); MbarInit(emptyC + i, kDecoders); }
+    for (int i = 0; i < 2; i++) { MbarInit(fullB + i, kStagers); MbarInit(emptyB + i, 1); }
+    for (int i = 0; i < kCbBufs; i++) { MbarInit(fullC + i, kStagers); MbarInit(emptyC + i, kDecoders); }
     MbarInit(doneBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -187,43 +191,60 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   if (warp >= 5) {
     // =========================== stagers ===========================
     const int st = tid - kStager0;
-    for (int kc = 0; kc < nChunks; kc++) {
-      const int buf = kc & 1;
-      if (kc >= 2) {
-        const uint32_t par = ((kc >> 1) - 1) & 1;
-        MbarWait(emptyB + buf, par);
-        MbarWait(emptyC + buf, par);
-      }
+    // chunk kc: positions (raw) + codebook slices + index rows, all by cp.async (one group)
+    auto fetchChunk = [&](int kc) {
+      const int cbuf = kc % kCbBufs;
       if (a.mode == 0) {
+        // per-chunk scalars: the two 4-channel halves, their subspaces and the offsets inside the codewords
+        const int taps = a.ksz * a.ksz;
+        const int chA = kc * 8, chB = kc * 8 + 4;
+        const bool okA = chA < a.Cg, okB = chB < a.Cg;
+        const int sA = okA ? chA / a.d : 0, jA = okA ? chA - sA * a.d : 0;
+        const int sB = okB ? chB / a.d : 0, jB = okB ? chB - sB * a.d : 0;
         // positions: float4 p = (half, pos): channels [kc*8 + half*4, +4) of the group
+        const float* srcG = srcBase + g * a.Cg + chA;
+#pragma unroll 2
         for (int p = st; p < a.planeF4; p += kStagers) {
           const int off = posoff[p];
-          const int ch = kc * 8 + (p >= a.NPOS ? 4 : 0);
-          const bool ok = off >= 0 && ch < a.Cg;
-          CpAsync16(raw + p, srcBase + g * a.Cg + (ok ? off + ch : 0), ok);
+          const bool hb = p >= a.NPOS;
+          const bool ok = off >= 0 && (hb ? okB : okA);
+          CpAsync16(raw + p, srcG + (ok ? off + (hb ? 4 : 0) : 0), ok);
         }
-        // codebook slices: slot = half; indices: rows [half][tap]
-        const int taps = a.ksz * a.ksz;
-        for (int e = st; e < 2 * K; e += kStagers) {
-          const int half = e >= K ? 1 : 0, k = e - half * K;
-          const int ch = kc * 8 + half * 4;
-          const bool ok = ch < a.Cg;
-          const int s = ok ? ch / a.d : 0, j0 = ok ? ch - s * a.d : 0;
-          CpAsync16(cbs + (buf * a.cbSlots + half) * K + k, a.ctrd + (static_cast<size_t>(s) * K + k) * a.d + j0, ok);
+        // codebook slices: slot = half
+        const float* cA = a.ctrd + static_cast<size_t>(sA) * K * a.d + jA;
+        const float* cB = a.ctrd + static_cast<size_t>(sB) * K * a.d + jB;
+        float4* cdst = cbs + cbuf * a.cbSlots * K;
+        for (int k = st; k < K; k += kStagers) {
+          CpAsync16(cdst + k, cA + static_cast<size_t>(k) * a.d, okA);
+          CpAsync16(cdst + K + k, cB + static_cast<size_t>(k) * a.d, okB);
         }
-        const int gran = CTv >> 4;   // 16-byte granules of valid channels per row
-        for (int e = st; e < 2 * taps * gran; e += kStagers) {
-          const int row = e / gran, q = e - row * gran;
-          const int half = row >= taps ? 1 : 0, tap = row - half * taps;
-          const int ch = kc * 8 + half * 4;
-          const int s = ch < a.Cg ? ch / a.d : 0;
-          const uint8_t* gsrc = a.asmt + (static_cast<size_t>(g * a.S + s) * taps + tap) * a.KgPad + ch0 + (q << 4);
-          CpAsync16(ids + (buf * a.idRows + row) * 128 + (q << 4), gsrc, true);
+        // index rows [half][tap]: stager warp w takes rows w, w+3, ...; lane < gran copies one 16-byte granule
+        const int gran = CTv >> 4;
+        if (lane < gran) {
+          const uint8_t* asA = a.asmt + static_cast<size_t>(g * a.S + sA) * taps * a.KgPad + ch0 + (lane << 4);
+          const uint8_t* asB = a.asmt + static_cast<size_t>(g * a.S + sB) * taps * a.KgPad + ch0 + (lane << 4);
+          uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
+          for (int row = warp - 5; row < 2 * taps; row += 3) {
+            const bool hb = row >= taps;
+            const int tap = hb ? row - taps : row;
+            CpAsync16(idst + row * 128, (hb ? asB : asA) + static_cast<size_t>(tap) * a.KgPad, true);
+          }
         }
       }
       CpAsyncCommit();
+    };
+    fetchChunk(0);
+    long long sCp = 0, sEB = 0, sEC = 0, sT0 = clock64();
+    for (int kc = 0; kc < nChunks; kc++) {
+      const int buf = kc & 1;
+      long long c0 = clock64();
       CpAsyncWaitAll();
-      asm volatile("bar.sync 1, 96;" ::: "memory");     // every stager's raw positions have landed
+      asm volatile("bar.sync 1, 96;" ::: "memory");     // every stager's copies of chunk kc have landed
+      sCp += clock64() - c0;
+      MbarArrive(fullC + kc % kCbBufs);                  // the decoders may start on chunk kc
+      c0 = clock64();
+      if (kc >= 2) MbarWait(emptyB + buf, ((kc >> 1) - 1) & 1);   // planes last read by the MMAs of chunk kc-2
+      sEB += clock64() - c0;
       float4* pHi = planes + (buf * 2 + 0) * a.planeF4;
       float4* pLo = planes + (buf * 2 + 1) * a.planeF4;
       for (int p = st; p < a.planeF4; p += kStagers) {
@@ -233,8 +254,21 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         pLo[p] = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // planes are read by the tensor core
-      MbarArrive(fullBC + buf);
+      MbarArrive(fullB + buf);
       asm volatile("bar.sync 1, 96;" ::: "memory");     // raw may be overwritten
+      if (kc + 1 < nChunks) {
+        const int nb = (kc + 1) % kCbBufs;
+        c0 = clock64();
+        if (kc + 1 >= kCbBufs) MbarWait(emptyC + nb, (((kc + 1) / kCbBufs) - 1) & 1);
+        sEC += clock64() - c0;
+        fetchChunk(kc + 1);
+      }
+    }
+    if (a.dbg && st == 0) {
+      atomicAdd(a.dbg + 8, static_cast<unsigned long long>(clock64() - sT0));
+      atomicAdd(a.dbg + 9, static_cast<unsigned long long>(sCp));
+      atomicAdd(a.dbg + 10, static_cast<unsigned long long>(sEB));
+      atomicAdd(a.dbg + 11, static_cast<unsigned long long>(sEC));
     }
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
@@ -244,16 +278,21 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       const uint64_t descFixed = (static_cast<uint64_t>(8) << 32) | (static_cast<uint64_t>(1) << 46);  // SBO = 128 B
       int t = 0;
       uint32_t acc = 0;
+      long long wBC = 0, wA = 0, tStart = clock64();
       for (int kc = 0; kc < nChunks; kc++) {
         const int buf = kc & 1;
-        MbarWait(fullBC + buf, (kc >> 1) & 1);
+        long long c0 = clock64();
+        MbarWait(fullB + buf, (kc >> 1) & 1);
+        wBC += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dHi = descFixed | ((SmemU32(planes + (buf * 2 + 0) * a.planeF4) >> 4) & 0x3FFFu);
         const uint64_t dLo = descFixed | ((SmemU32(planes + (buf * 2 + 1) * a.planeF4) >> 4) & 0x3FFFu);
         const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0], ne = a.chunkCount[a.mode == 1 ? kc : 0];
         for (int s0 = 0; s0 < ne; s0 += GT, t++) {
           const int slot = t % NSLOT;
+          c0 = clock64();
           MbarWait(fullA + slot, (t / NSLOT) & 1);
+          wA += clock64() - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int n = min(GT, ne - s0);
           for (int i = 0; i < n; i++) {
@@ -271,6 +310,16 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         UmmaCommit(emptyB + buf);
       }
       UmmaCommit(doneBar);
+      if (a.dbg) {
+        const long long tIssue = clock64() - tStart;
+        long long c0 = clock64();
+        MbarWait(doneBar, 0);
+        atomicAdd(a.dbg + 0, static_cast<unsigned long long>(tIssue));
+        atomicAdd(a.dbg + 1, static_cast<unsigned long long>(wBC));
+        atomicAdd(a.dbg + 2, static_cast<unsigned long long>(wA));
+        atomicAdd(a.dbg + 3, static_cast<unsigned long long>(clock64() - c0));
+                atomicAdd(a.dbg + 5, 1ull);
+      }
     }
   } else {
     // =========================== decoders ===========================
@@ -278,16 +327,21 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
     const int cc = min(c, CTv - 1);                 // rows beyond the valid channels decode a copy (never stored)
     const uint32_t laneBase = static_cast<uint32_t>(warp * 32) << 16;
     int t = 0;
+    long long dFC = 0, dEA = 0, dT0 = clock64();
     for (int kc = 0; kc < nChunks; kc++) {
-      const int buf = kc & 1;
-      MbarWait(fullBC + buf, (kc >> 1) & 1);
-      const uint8_t* idb = ids + buf * a.idRows * 128 + cc;
-      const float4* cb = cbs + buf * a.cbSlots * K;
+      const int cbuf = kc % kCbBufs;
+      long long c0 = clock64();
+      MbarWait(fullC + cbuf, (kc / kCbBufs) & 1);
+      dFC += clock64() - c0;
+      const uint8_t* idb = ids + cbuf * a.idRows * 128 + cc;
+      const float4* cb = cbs + cbuf * a.cbSlots * K;
       const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0], ne = a.chunkCount[a.mode == 1 ? kc : 0];
       for (int s0 = 0; s0 < ne; s0 += GT, t++) {
         const int slot = t % NSLOT;
         if (t >= NSLOT) {
+          c0 = clock64();
           MbarWait(emptyA + slot, ((t / NSLOT) - 1) & 1);
+          dEA += clock64() - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const int n = min(GT, ne - s0);
@@ -314,7 +368,12 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         MbarArrive(fullA + slot);
       }
-      MbarArrive(emptyC + buf);
+      MbarArrive(emptyC + cbuf);
+    }
+    if (a.dbg && tid == 0) {
+      atomicAdd(a.dbg + 12, static_cast<unsigned long long>(clock64() - dT0));
+      atomicAdd(a.dbg + 13, static_cast<unsigned long long>(dFC));
+      atomicAdd(a.dbg + 14, static_cast<unsigned long long>(dEA));
     }
   }
 
@@ -420,8 +479,24 @@ int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N
   const long long blocks = static_cast<long long>(CeilDiv(N * a.IB, a.NT)) * a.G * a.nct;
   QCNN_CHECK(blocks <= 2147483647LL, "qcnn_conv_aprx_forward: batch too large for the tensor-core tiling");
   QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  static const bool dbg = getenv("QCNN_GEMM_DBG") != nullptr;
+  if (dbg) {
+    QCNN_CUDA(cudaMalloc(&a.dbg, 128));
+    QCNN_CUDA(cudaMemsetAsync(a.dbg, 0, 128, st));
+  }
   pq_gemm_tc_kernel<<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
   QCNN_CUDA(cudaGetLastError());
+  if (dbg) {
+    unsigned long long h[16];
+    QCNN_CUDA(cudaStreamSynchronize(st));
+    QCNN_CUDA(cudaMemcpy(h, a.dbg, 128, cudaMemcpyDeviceToHost));
+    const double n = h[5] ? static_cast<double>(h[5]) : 1.0;
+    fprintf(stderr, "[pq_gemm dbg] ctas=%llu NT=%d GT=%d chunks=%d ksteps=%d | per CTA: issue-loop %.0f clk (wait planes %.0f, wait weights %.0f), "
+            "drain %.0f | stager loop %.0f (wait copies %.0f, wait planes free %.0f, wait cb free %.0f) | decoder loop %.0f (wait cb %.0f, "
+            "wait ring %.0f)\n", h[5], a.NT, a.GT, a.nChunks, a.chunkCount[0], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[8] / n, h[9] / n,
+            h[10] / n, h[11] / n, h[12] / n, h[13] / n, h[14] / n);
+    cudaFree(a.dbg);
+  }
   return 0;
 }
 

@@ -93,7 +93,7 @@ __device__ __forceinline__ void SplitTf32x4(const float4 v, float4& hi, float4& 
 }
 
 struct SmemMap {  // byte offsets inside the dynamic shared memory
-  int planes, raw, cbs, ids, tab, posoff, outoff, bias, bars, tmem, total;
+  int planes, raw, cbs, ids, tab, posoff, posrow, outoff, bias, bars, tmem, total;
 };
 __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   SmemMap m;
@@ -104,6 +104,7 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   m.ids = o;    o += kCbBufs * a.idRows * 128;          // [cbuf][row][128 channels] assignment indices
   m.tab = o;    o += a.ntab * 16;
   m.posoff = o; o += a.planeF4 * 4;                     // source element offset of every staged float4 (-1: zero)
+  m.posrow = o; o += a.mode == 1 ? a.planeF4 * 4 : 0;   // mode 1: first input row of the position (phase row 0)
   m.outoff = o; o += 256 * 4;                           // destination element offset of every position (-1: none)
   m.bias = o;   o += 128 * 4;
   m.bars = o;   o += 8 * (2 * kMaxSlots + 2 * kCbBufs + 5);
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   uint8_t* ids = smem + sm.ids;
   KStep* tabS = reinterpret_cast<KStep*>(smem + sm.tab);
   int* posoff = reinterpret_cast<int*>(smem + sm.posoff);
+  int* posrow = reinterpret_cast<int*>(smem + sm.posrow);
   int* outoff = reinterpret_cast<int*>(smem + sm.outoff);
   float* biasS = reinterpret_cast<float*>(smem + sm.bias);
   uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + sm.bars);   // [kMaxSlots] decoders -> issuer
@@ -157,6 +159,18 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       const int i = F / a.IB, rem = F - i * a.IB;
       const int r = rem / a.PW, c = rem - r * a.PW;
       if (i < a.N && r >= a.pad && c >= a.pad) off = (((i - i0) * a.Hi + (r - a.pad)) * a.Wi + (c - a.pad)) * a.Cin;
+    } else if (a.mode == 1) {
+      // float4 p: phase column pw = p / NPOS, position = p % NPOS -> pixel (r*stride + ph - pad, c*stride + pw - pad);
+      // the phase row ph is the chunk, so the row part is resolved per chunk from posrow
+      const int pw = p / a.NPOS, pos = p - pw * a.NPOS;
+      const int F = Q0 + pos;
+      const int i = F / a.IB, rem = F - i * a.IB;
+      const int r = rem / a.PW, c = rem - r * a.PW;
+      const int wi = c * a.stride + pw - a.pad;
+      const bool colOk = i < a.N && wi >= 0 && wi < a.Wi;
+      off = static_cast<int>((i - i0) * a.srcImg) + (r * a.stride - a.pad) * a.rowStride + wi * a.colStride;
+      posrow[p] = colOk ? r * a.stride - a.pad : -(1 << 28);
+      raw[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // components beyond Cg stay zero
     }
     posoff[p] = off;
   }
@@ -228,6 +242,35 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
             const bool hb = row >= taps;
             const int tap = hb ? row - taps : row;
             CpAsync16(idst + row * 128, (hb ? asB : asA) + static_cast<size_t>(tap) * a.KgPad, true);
+          }
+        }
+      }
+      if (a.mode == 1) {
+        // chunk = phase row ph: pixels of input rows r*stride + ph - pad, one 4-byte copy per channel
+        const int ph = kc;
+        const float* srcG = srcBase + static_cast<size_t>(g) * a.Cg * a.chStride + ph * a.rowStride;
+#pragma unroll 2
+        for (int p = st; p < a.planeF4; p += kStagers) {
+          const bool ok = static_cast<unsigned>(posrow[p] + ph) < static_cast<unsigned>(a.Hi);
+          const float* px = srcG + (ok ? posoff[p] : 0);
+          float* dstp = reinterpret_cast<float*>(raw + p);
+          for (int ch = 0; ch < a.Cg; ch++) CpAsync4(dstp + ch, px + ch * a.chStride, ok);
+        }
+        // codebook: slot 0 = the first 4 floats of every codeword of subspace 0, slot 1 = zeros (unpaired taps)
+        float4* cdst = cbs + cbuf * a.cbSlots * K;
+        for (int k = st; k < K; k += kStagers) {
+          CpAsync16(cdst + k, a.ctrd + static_cast<size_t>(k) * a.d, true);
+          CpAsync16(cdst + K + k, a.ctrd, false);
+        }
+        // index rows of the taps with kh % stride == ph, in (kh, kw) order
+        const int gran = CTv >> 4;
+        if (lane < gran) {
+          const uint8_t* as0 = a.asmt + static_cast<size_t>(g * a.S) * a.ksz * a.ksz * a.KgPad + ch0 + (lane << 4);
+          uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
+          const int nrow = ((a.ksz - ph + a.stride - 1) / a.stride) * a.ksz;
+          for (int row = warp - 5; row < nrow; row += 3) {
+            const int kh = ph + (row / a.ksz) * a.stride, kw = row % a.ksz;
+            CpAsync16(idst + row * 128, as0 + static_cast<size_t>(kh * a.ksz + kw) * a.KgPad, true);
           }
         }
       }
@@ -420,9 +463,66 @@ namespace qcnn {
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands) {
   if (getenv("QCNN_NO_DECTC") != nullptr) return;
   const int G = L->grp, Cg = L->Cin / G, Kg = L->Cout / G, taps = L->ksz * L->ksz;
-  if (L->stride != 1 || L->src_nchw) return;
-  if (L->d % 4 != 0 || Cg % 4 != 0 || L->Cin % 4 != 0 || L->S * L->d < Cg) return;
-  if (L->K < 1 || L->K > 256 || Kg % 16 != 0 || taps > kMaxKSteps) return;
+  if (L->K < 1 || L->K > 256 || Kg % 16 != 0) return;
+  const size_t smemMax0 = L->ctx->smem_optin ? L->ctx->smem_optin : 227 * 1024;
+  if (L->stride > 1) {
+    // mode 1: strided convolution with one subspace over <= 4 input channels (conv1), input on stride x stride phase planes
+    const int st = L->stride, rowsPer = CeilDiv(L->ksz, st);
+    if (Cg > 4 || L->S != 1 || L->d < Cg || st > 8 || L->Wo > CeilDiv(L->Win + 2 * L->pad, st)) return;
+    const int pairs = (L->ksz + 1) / 2;
+    if (rowsPer * pairs > 32 || L->ksz * pairs > kMaxKSteps) return;
+    const int PWp = CeilDiv(L->Win + 2 * L->pad, st), PHp = CeilDiv(L->Hin + 2 * L->pad, st);
+    const int IB = PHp * PWp;
+    if (static_cast<double>(N) * IB > 2.0e9 || static_cast<double>(L->Hin) * L->Win * L->Cin * 4 > 2.0e9) return;
+    const int nts1[2] = {256, 128};
+    for (int ni = 0; ni < 2; ni++) {
+      const int NT = nts1[ni];
+      const int gts1[3] = {6, 4, 8};
+      for (int gi = 0; gi < 3; gi++) {
+        const int GT = gts1[gi];
+        ConvPlan p;
+        memset(&p, 0, sizeof(p));
+        p.kernel = 6; p.CPT = NT; p.J = GT; p.threads = kThreads;
+        GemmArgs& ga = p.g;
+        ga.mode = 1;
+        ga.PW = PWp; ga.IB = IB; ga.NT = NT; ga.GT = GT; ga.NSLOT = std::min(kMaxSlots, 16 / GT);
+        ga.NPOS = RoundUp(NT + ((L->ksz - 1) / st) * (PWp + 1), 8);
+        ga.planeF4 = st * ga.NPOS;
+        ga.cbSlots = 2; ga.idRows = rowsPer * L->ksz;
+        ga.nChunks = st;
+        ga.K = L->K;
+        ga.nct = CeilDiv(Kg, 128);
+        int ne = 0;
+        for (int ph = 0; ph < st; ph++) {
+          ga.chunkFirst[ph] = ne;
+          for (int kh = ph; kh < L->ksz; kh += st)
+            for (int kw = 0; kw < L->ksz; kw += 2, ne++) {
+              if (ne >= kMaxKSteps) { ne = kMaxKSteps + 1000; break; }
+              KStep& ks = ga.tab[ne];
+              const bool paired = kw + 1 < L->ksz && (kw % st) + 1 < st;   // partner in the next phase column, same shift
+              ks.bStart = (kw % st) * ga.NPOS + (kh / st) * PWp + kw / st;
+              ks.lbo = paired ? ga.NPOS : 1;
+              ks.idx0 = static_cast<short>((kh - ph) / st * L->ksz + kw);
+              ks.idx1 = static_cast<short>(paired ? ks.idx0 + 1 : ks.idx0);
+              ks.cb0 = 0; ks.cb1 = paired ? 0 : 1;
+              if (!paired && kw + 1 < L->ksz) kw--;   // the partner starts its own k-step
+            }
+          ga.chunkCount[ph] = ne - ga.chunkFirst[ph];
+        }
+        if (ne > kMaxKSteps) continue;
+        ga.ntab = ne;
+        p.smem = static_cast<size_t>(MapSmem(ga).total);
+        if (p.smem > smemMax0) continue;
+        p.a.CT = 128; p.a.nct = ga.nct; p.a.R = NT; p.a.nstrips = GT; p.a.rgroups = 1;
+        const double perCta = ne * 3.0 * (NT / 2.0) * 1.15 + 120.0 * ne / GT + 9000.0 + NT * 24.0;
+        const double ctas = static_cast<double>(CeilDiv(N * IB, NT)) * G * ga.nct;
+        cands->emplace_back(perCta * std::ceil(ctas / L->ctx->sm_count), p);
+      }
+    }
+    return;
+  }
+  if (L->src_nchw) return;
+  if (L->d % 4 != 0 || Cg % 4 != 0 || L->Cin % 4 != 0 || L->S * L->d < Cg || taps > kMaxKSteps) return;
   const int PW = L->Win + L->pad, IB = (L->Hin + L->pad) * PW;
   if (L->Ho > L->Hin + L->pad || L->Wo > PW) return;
   if (static_cast<double>(N) * IB > 2.0e9) return;
@@ -475,6 +575,8 @@ int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N
   a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = L->grp; a.Cg = L->Cin / L->grp; a.Kg = L->Cout / L->grp;
   a.KgPad = RoundUp(a.Kg, 16); a.S = L->S; a.K = L->K; a.d = L->d;
   a.srcImg = static_cast<long long>(a.Hi) * a.Wi * a.Cin;
+  if (L->src_nchw) { a.rowStride = a.Wi; a.colStride = 1; a.chStride = a.Hi * a.Wi; }
+  else { a.rowStride = a.Wi * a.Cin; a.colStride = a.Cin; a.chStride = 1; }
   a.dstImg = static_cast<long long>(a.Ho) * a.Wo * a.Cout;
   const long long blocks = static_cast<long long>(CeilDiv(N * a.IB, a.NT)) * a.G * a.nct;
   QCNN_CHECK(blocks <= 2147483647LL, "qcnn_conv_aprx_forward: batch too large for the tensor-core tiling");

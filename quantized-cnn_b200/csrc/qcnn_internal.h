@@ -105,6 +105,7 @@ struct GemmArgs {
   int N, Hi, Wi, Cin, Ho, Wo, Cout, ksz, pad, stride, G, Cg, Kg, KgPad, S, K, d;
   int mode;                   // 0 stride-1 conv, 1 strided conv on phase planes, 2 fully connected
   int PW, IB;                 // flat grid: row pitch / positions per image
+  int rowStride, colStride, chStride;   // mode 1: source element strides of an input row / column / channel
   int NT;                     // positions per CTA = MMA N (multiple of 16, <= 256)
   int NPOS;                   // staged positions per plane (NT + halo)
   int planeF4;                // float4 per staged plane set (one of hi / lo, one buffer)

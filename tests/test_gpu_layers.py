@@ -111,6 +111,8 @@ CONV_CASES = [
     (1, 13, 13, 256, 384, 3, 1, 1, 1, 16, 64, 16),    # sweep point S=16, K=64, d=16
     (2, 31, 29, 8, 32, 7, 0, 2, 1, 2, 128, 4),        # VggCnnS-like stride 2, S>1
     (1, 20, 20, 16, 32, 5, 2, 3, 2, 2, 32, 4),        # stride 3 with padding and groups
+    (2, 17, 19, 3, 32, 5, 1, 2, 1, 1, 64, 4),         # conv1-like: 3 input channels, stride 2 with padding, one subspace
+    (3, 14, 14, 4, 48, 3, 0, 3, 1, 1, 128, 4),        # 4 input channels, stride 3, one subspace
 ]
 
 

@@ -19,6 +19,10 @@
 //     exactly the reference's (bias, then s ascending) and the result is bit-identical to the CPU path.
 #include "qcnn_internal.h"
 
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 namespace {
 
 constexpr int kFcThreads = 256;
@@ -233,6 +237,15 @@ __global__ void fc_reduce_kernel(const float* __restrict__ partial, float* __res
   dst[i] = relu ? fmaxf(v, 0.0f) : v;
 }
 
+// dst[n][f] = src[n*Din + srcoff[f]]: NHWC-mapped source -> the flat [N][Din] rows the tensor-core path stages
+__global__ void fc_flatten_kernel(const float* __restrict__ src, const int* __restrict__ srcoff, float* __restrict__ dst,
+                                  int N, int Din) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(N) * Din) return;
+  const int n = static_cast<int>(i / Din), f = static_cast<int>(i - static_cast<size_t>(n) * Din);
+  dst[i] = __ldg(src + static_cast<size_t>(n) * Din + __ldg(srcoff + f));
+}
+
 template <int K, int CPT, int TN, int PF, bool PRE>
 int Launch(const FcArgs& a, dim3 grid, cudaStream_t st) {
   const size_t xpad = (static_cast<size_t>(TN) * PF * a.d + 3) & ~static_cast<size_t>(3);
@@ -268,9 +281,97 @@ static int ChunkLen(int K, int tn) {
   return K <= 32 ? 32 : (K <= 64 ? 16 : 8);
 }
 
+// Large batches: the layer as a decode-at-use GEMM on the tensor cores (pq_gemm_tc.cu, mode 2): M = 128 outputs per CTA,
+// N = up to 256 images, K split over CTAs so that the grid fills the GPU; partial sums are reduced in fixed order by
+// fc_reduce_kernel.  QCNN_FC_TC=0 keeps the gather kernel, QCNN_FC_TC=1 forces the tensor-core path for any N.
+int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st, bool* handled) {
+  *handled = false;
+  static const char* env = getenv("QCNN_FC_TC");
+  if (env && env[0] == '0') return 0;
+  if (!(env && env[0] == '1') && N < 96) return 0;
+  if (L->opt_fc_nsplit || L->opt_fc_tn) return 0;   // explicit gather-kernel tuning (fc_nsplit = 1: bit-exact reference order)
+  if (L->Din % 8 != 0 || !(L->d == 1 || L->d % 4 == 0) || L->S * L->d < L->Din || L->K > 256 || L->K % 4 != 0) return 0;
+  qcnn_ctx* ctx = L->ctx;
+  const float* x = src;
+  if (L->d_srcoff) {
+    const size_t need = sizeof(float) * static_cast<size_t>(N) * L->Din;
+    if (need > L->flat_bytes) {
+      if (L->d_flat) QCNN_CUDA(cudaFree(L->d_flat));
+      L->d_flat = nullptr; L->flat_bytes = 0;
+      QCNN_CUDA(cudaMalloc(&L->d_flat, need));
+      L->flat_bytes = need;
+    }
+    const size_t total = static_cast<size_t>(N) * L->Din;
+    fc_flatten_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, L->d_srcoff, L->d_flat, N, L->Din);
+    QCNN_CUDA(cudaGetLastError());
+    ctx->launches++;
+    x = L->d_flat;
+  }
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 2;
+  a.src = x; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
+  a.N = N; a.Cin = L->Din; a.Cout = L->Dout; a.G = 1; a.Cg = L->Din; a.Kg = L->Dout; a.KgPad = L->DoutPad;
+  a.S = L->S; a.K = L->K; a.d = L->d; a.kshift = L->kshift;
+  a.srcImg = L->Din; a.dstImg = 0;
+  a.IB = 1; a.PW = 1;
+  a.NT = std::min(256, RoundUp(N, 16));
+  const int KS = 4;
+  a.GT = 4; a.NSLOT = 4;
+  a.planeF4 = KS * 2 * a.NT;
+  a.NPOS = a.NT;
+  a.cbSlots = L->d == 1 ? 8 * KS : 2 * KS;
+  a.idRows = a.cbSlots;
+  a.cbF4 = L->d == 1 ? L->K / 4 : L->K;
+  a.ntab = KS;
+  a.chunkFirst[0] = 0; a.chunkCount[0] = KS;
+  for (int i = 0; i < KS; i++) {
+    KStep& ks = a.tab[i];
+    ks.bStart = 2 * i * a.NT; ks.lbo = a.NT;
+    if (L->d == 1) { ks.idx0 = static_cast<short>(8 * i); ks.idx1 = static_cast<short>(8 * i + 4); }
+    else { ks.idx0 = static_cast<short>(2 * i); ks.idx1 = static_cast<short>(2 * i + 1); }
+    ks.cb0 = ks.idx0; ks.cb1 = ks.idx1;
+  }
+  a.nct = CeilDiv(L->Dout, 128);
+  const int tiles = CeilDiv(N, a.NT);
+  a.kAll = L->Din / 8;
+  int nsplit = std::max(1, ctx->sm_count / (tiles * a.nct));
+  a.kPerSplit = RoundUp(CeilDiv(a.kAll, nsplit), KS);
+  nsplit = CeilDiv(a.kAll, a.kPerSplit);
+  a.nsplit = nsplit;
+  a.dstRow = nsplit > 1 ? L->DoutPad : L->Dout;
+  a.relu = nsplit > 1 ? 0 : relu;
+  if (PqGemmSmemBytes(a) > (ctx->smem_optin ? ctx->smem_optin : 227 * 1024)) return 0;
+  if (nsplit > 1) {
+    const size_t need = sizeof(float) * static_cast<size_t>(nsplit) * N * L->DoutPad;
+    if (need > L->partial_bytes) {
+      if (L->d_partial) QCNN_CUDA(cudaFree(L->d_partial));
+      L->d_partial = nullptr; L->partial_bytes = 0;
+      QCNN_CUDA(cudaMalloc(&L->d_partial, need));
+      L->partial_bytes = need;
+    }
+    a.partial = L->d_partial;
+  }
+  if (int rc = LaunchPqGemmArgs(a, static_cast<long long>(tiles) * nsplit * a.nct, st)) return rc;
+  ctx->launches++;
+  if (nsplit > 1) {
+    const int total = N * L->Dout;
+    fc_reduce_kernel<<<CeilDiv(total, 256), 256, 0, st>>>(a.partial, dst, N, L->Dout, L->DoutPad, nsplit, relu);
+    QCNN_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  *handled = true;
+  return 0;
+}
+
 int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st) {
   QCNN_CHECK(L->kind == QCNN_KIND_FC, "qcnn_fc_aprx_forward: layer is not fully-connected");
   QCNN_CHECK(N >= 1, "qcnn_fc_aprx_forward: N must be >= 1");
+  {
+    bool handled = false;
+    if (int rc = LaunchFcTc(L, src, N, dst, relu, st, &handled)) return rc;
+    if (handled) return 0;
+  }
   qcnn_ctx* ctx = L->ctx;
   FcArgs a;
   a.src = src; a.dst = dst; a.partial = nullptr;

@@ -100,7 +100,7 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   int o = 0;
   m.planes = o; o += 2 * 2 * a.planeF4 * 16;            // [buf][hi,lo][planeF4]
   m.raw = o;    o += a.planeF4 * 16;                    // cp.async target of the positions
-  m.cbs = o;    o += kCbBufs * a.cbSlots * a.K * 16;    // [cbuf][slot][K] codeword halves (raw fp32)
+  m.cbs = o;    o += kCbBufs * a.cbSlots * a.cbF4 * 16; // [cbuf][slot][cbF4] codeword pieces (raw fp32)
   m.ids = o;    o += kCbBufs * a.idRows * 128;          // [cbuf][row][128 channels] assignment indices
   m.tab = o;    o += a.ntab * 16;
   m.posoff = o; o += a.planeF4 * 4;                     // source element offset of every staged float4 (-1: zero)
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   extern __shared__ __align__(128) unsigned char smem[];
   const SmemMap sm = MapSmem(a);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int K = a.K, NT = a.NT, GT = a.GT, NSLOT = a.NSLOT, nChunks = a.nChunks;
+  const int K = a.K, NT = a.NT, GT = a.GT, NSLOT = a.NSLOT;
 
   float4* planes = reinterpret_cast<float4*>(smem + sm.planes);
   float4* raw = reinterpret_cast<float4*>(smem + sm.raw);
@@ -138,15 +138,21 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   uint32_t* tmemBase = reinterpret_cast<uint32_t*>(smem + sm.tmem);
 
   int b = blockIdx.x;
-  const int gc = b % (a.G * a.nct);
-  const int tile = b / (a.G * a.nct);
-  const int ct = gc % a.nct, g = gc / a.nct;
+  const int ct = b % a.nct; b /= a.nct;
+  int g = 0, split = 0;
+  if (a.mode == 2) { split = b % a.nsplit; b /= a.nsplit; } else { g = b % a.G; b /= a.G; }
+  const int tile = b;
   const int ch0 = ct * 128;                            // first channel of the tile inside the group
   const int CTv = min(128, a.Kg - ch0);                // valid channels
   const int Q0 = tile * NT;                            // first flat position
   const int i0 = Q0 / a.IB;                            // first image touched
   const float* srcBase = a.src + static_cast<size_t>(i0) * a.srcImg;
   float* dstBase = a.dst + static_cast<size_t>(i0) * a.dstImg + g * a.Kg + ch0;
+  // mode 2: this CTA's k-step range [k0, k0 + kTotal) of the layer; partial sums go to their own plane
+  const int k0 = split * a.kPerSplit;
+  const int kTotal = a.mode == 2 ? min(a.kPerSplit, a.kAll - k0) : 0;
+  const int nChunks = a.mode == 2 ? (kTotal + a.chunkCount[0] - 1) / a.chunkCount[0] : a.nChunks;
+  if (a.mode == 2 && a.nsplit > 1) dstBase = a.partial + (static_cast<size_t>(split) * a.N + Q0) * a.dstRow + ch0;
 
   // ---- set-up (all threads) ----
   for (int e = tid; e < a.ntab; e += kThreads) tabS[e] = a.tab[e];
@@ -171,6 +177,10 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       off = static_cast<int>((i - i0) * a.srcImg) + (r * a.stride - a.pad) * a.rowStride + wi * a.colStride;
       posrow[p] = colOk ? r * a.stride - a.pad : -(1 << 28);
       raw[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // components beyond Cg stay zero
+    } else {
+      // float4 p = ((k-step i, half), image n): features [8i + 4 half, +4) of the chunk, image Q0 + n
+      const int n = p % NT, ih = p / NT;
+      if (Q0 + n < a.N) off = n * a.Cin + ih * 4;
     }
     posoff[p] = off;
   }
@@ -180,11 +190,12 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       const int Q = Q0 + p;
       const int i = Q / a.IB, rem = Q - i * a.IB;
       const int ho = rem / a.PW, wo = rem - ho * a.PW;
-      if (i < a.N && ho < a.Ho && wo < a.Wo) off = (((i - i0) * a.Ho + ho) * a.Wo + wo) * a.Cout;
+      if (a.mode == 2) { if (Q < a.N) off = p * a.dstRow; }
+      else if (i < a.N && ho < a.Ho && wo < a.Wo) off = (((i - i0) * a.Ho + ho) * a.Wo + wo) * a.Cout;
     }
     outoff[p] = off;
   }
-  for (int c = tid; c < 128; c += kThreads) biasS[c] = c < CTv ? __ldg(a.bias + g * a.Kg + ch0 + c) : 0.0f;
+  for (int c = tid; c < 128; c += kThreads) biasS[c] = (c < CTv && split == 0) ? __ldg(a.bias + g * a.Kg + ch0 + c) : 0.0f;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmemBase)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -274,6 +285,47 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
           }
         }
       }
+      if (a.mode == 2) {
+        // chunk = KS consecutive k-steps of this CTA's range: features [f0, f0 + 8 ne)
+        const int KS = a.chunkCount[0];
+        const int ne = min(KS, kTotal - kc * KS);
+        const int f0 = (k0 + kc * KS) * 8;
+        const float* srcG = srcBase + f0;
+        const int lim = ne * 2 * NT;          // float4 beyond the chunk's k-steps are not read by any MMA
+#pragma unroll 2
+        for (int p = st; p < lim; p += kStagers) {
+          const int off = posoff[p];
+          CpAsync16(raw + p, srcG + (off >= 0 ? off : 0), off >= 0);
+        }
+        const int gran = (CTv + 15) >> 4;
+        if (a.d == 1) {
+          // slot q = subspace f0 + q: its K scalar codewords; index row q
+          const int kq = K >> 2;
+          float4* cdst = cbs + cbuf * a.cbSlots * a.cbF4;
+          for (int e = st; e < 8 * ne * kq; e += kStagers) CpAsync16(cdst + e, a.ctrd + static_cast<size_t>(f0) * K + e * 4, true);
+          if (lane < gran) {
+            const uint8_t* as0 = a.asmt + static_cast<size_t>(f0) * a.KgPad + ch0 + (lane << 4);
+            uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
+            for (int row = warp - 5; row < 8 * ne; row += 3) CpAsync16(idst + row * 128, as0 + static_cast<size_t>(row) * a.KgPad, true);
+          }
+        } else {
+          // slot q = features [f0 + 4q, +4): piece j0 of every codeword of subspace s; index row q = row s of the layer
+          float4* cdst = cbs + cbuf * a.cbSlots * a.cbF4;
+          for (int e = st; e < 2 * ne * K; e += kStagers) {
+            const int q = e / K, k = e - q * K;
+            const int f = f0 + 4 * q;
+            const int s = f / a.d, j0 = f - s * a.d;
+            CpAsync16(cdst + e, a.ctrd + (static_cast<size_t>(s) * K + k) * a.d + j0, true);
+          }
+          if (lane < gran) {
+            uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
+            for (int row = warp - 5; row < 2 * ne; row += 3) {
+              const int s = (f0 + 4 * row) / a.d;
+              CpAsync16(idst + row * 128, a.asmt + static_cast<size_t>(s) * a.KgPad + ch0 + (lane << 4), true);
+            }
+          }
+        }
+      }
       CpAsyncCommit();
     };
     fetchChunk(0);
@@ -330,7 +382,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dHi = descFixed | ((SmemU32(planes + (buf * 2 + 0) * a.planeF4) >> 4) & 0x3FFFu);
         const uint64_t dLo = descFixed | ((SmemU32(planes + (buf * 2 + 1) * a.planeF4) >> 4) & 0x3FFFu);
-        const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0], ne = a.chunkCount[a.mode == 1 ? kc : 0];
+        const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0];
+        const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kc : 0];
         for (int s0 = 0; s0 < ne; s0 += GT, t++) {
           const int slot = t % NSLOT;
           c0 = clock64();
@@ -377,8 +430,10 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       MbarWait(fullC + cbuf, (kc / kCbBufs) & 1);
       dFC += clock64() - c0;
       const uint8_t* idb = ids + cbuf * a.idRows * 128 + cc;
-      const float4* cb = cbs + cbuf * a.cbSlots * K;
-      const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0], ne = a.chunkCount[a.mode == 1 ? kc : 0];
+      const float4* cb = cbs + cbuf * a.cbSlots * a.cbF4;
+      const float* cbf = reinterpret_cast<const float*>(cb);
+      const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0];
+      const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kc : 0];
       for (int s0 = 0; s0 < ne; s0 += GT, t++) {
         const int slot = t % NSLOT;
         if (t >= NSLOT) {
@@ -390,10 +445,23 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         const int n = min(GT, ne - s0);
         for (int i = 0; i < n; i++) {
           const KStep ks = tabS[e0 + s0 + i];
-          const int i0x = idb[ks.idx0 * 128];
-          const int i1x = idb[ks.idx1 * 128];
-          const float4 w0 = cb[ks.cb0 * K + i0x];
-          const float4 w1 = cb[ks.cb1 * K + i1x];
+          float4 w0, w1;
+          if (a.d == 1) {
+            // scalar codewords: every feature is its own subspace (rows / slots idx0 .. idx0+3 and idx1 .. idx1+3)
+            const uint8_t* r0 = idb + ks.idx0 * 128;
+            const uint8_t* r1 = idb + ks.idx1 * 128;
+            const float* c0p = cbf + ks.cb0 * K;
+            const float* c1p = cbf + ks.cb1 * K;
+            w0.x = c0p[r0[0] >> a.kshift];           w0.y = c0p[K + (r0[128] >> a.kshift)];
+            w0.z = c0p[2 * K + (r0[256] >> a.kshift)]; w0.w = c0p[3 * K + (r0[384] >> a.kshift)];
+            w1.x = c1p[r1[0] >> a.kshift];           w1.y = c1p[K + (r1[128] >> a.kshift)];
+            w1.z = c1p[2 * K + (r1[256] >> a.kshift)]; w1.w = c1p[3 * K + (r1[384] >> a.kshift)];
+          } else {
+            const int i0x = idb[ks.idx0 * 128] >> a.kshift;
+            const int i1x = idb[ks.idx1 * 128] >> a.kshift;
+            w0 = cb[ks.cb0 * K + i0x];
+            w1 = cb[ks.cb1 * K + i1x];
+          }
           float4 h0, l0, h1, l1;
           SplitTf32x4(w0, h0, l0);
           SplitTf32x4(w1, h1, l1);
@@ -443,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         const int off = outoff[blk * 16 + j];
         if (off >= 0 && chOk) {
           float v = __uint_as_float(r[j]) + bv;
-          if (a.relu) v = fmaxf(v, 0.0f);
+          if (a.relu) v = fmaxf(v, 0.0f);   // (never set together with split-K partial sums)
           dstBase[off + c] = v;
         }
       }
@@ -490,7 +558,7 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
         ga.planeF4 = st * ga.NPOS;
         ga.cbSlots = 2; ga.idRows = rowsPer * L->ksz;
         ga.nChunks = st;
-        ga.K = L->K;
+        ga.K = L->K; ga.cbF4 = L->K;
         ga.nct = CeilDiv(Kg, 128);
         int ne = 0;
         for (int ph = 0; ph < st; ph++) {
@@ -553,7 +621,7 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
         ks.idx0 = static_cast<short>(t); ks.idx1 = static_cast<short>(taps + t);
         ks.cb0 = 0; ks.cb1 = 1;
       }
-      ga.K = L->K;
+      ga.K = L->K; ga.cbF4 = L->K;
       ga.nct = CeilDiv(Kg, 128);
       p.smem = static_cast<size_t>(MapSmem(ga).total);
       if (p.smem > smemMax) continue;
@@ -599,6 +667,17 @@ int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N
             h[10] / n, h[11] / n, h[12] / n, h[13] / n, h[14] / n);
     cudaFree(a.dbg);
   }
+  return 0;
+}
+
+// generic entry for callers that fill GemmArgs themselves (the fully-connected path in fc_aprx.cu)
+size_t PqGemmSmemBytes(const GemmArgs& a) { return static_cast<size_t>(MapSmem(a).total); }
+int LaunchPqGemmArgs(const GemmArgs& a, long long blocks, cudaStream_t st) {
+  const size_t smem = PqGemmSmemBytes(a);
+  QCNN_CHECK(blocks >= 1 && blocks <= 2147483647LL, "pq_gemm_tc: bad grid");
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pq_gemm_tc_kernel<<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(a);
+  QCNN_CUDA(cudaGetLastError());
   return 0;
 }
 

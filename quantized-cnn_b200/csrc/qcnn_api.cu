@@ -248,6 +248,7 @@ void qcnn_layer_destroy(qcnn_layer* L) {
   if (L->d_ctrd) cudaFree(L->d_ctrd);
   if (L->d_bias) cudaFree(L->d_bias);
   if (L->d_partial) cudaFree(L->d_partial);
+  if (L->d_flat) cudaFree(L->d_flat);
   if (L->d_srcoff) cudaFree(L->d_srcoff);
   delete L->cands;
   delete L->tunedPlans;

@@ -106,6 +106,11 @@ struct GemmArgs {
   int mode;                   // 0 stride-1 conv, 1 strided conv on phase planes, 2 fully connected
   int PW, IB;                 // flat grid: row pitch / positions per image
   int rowStride, colStride, chStride;   // mode 1: source element strides of an input row / column / channel
+  int nsplit, kAll, kPerSplit;  // mode 2: K splits, k-steps of the layer / per split (partial sums -> fc_reduce)
+  int kshift;                   // stored assignment byte = index << kshift
+  float* partial;               // mode 2, nsplit > 1: [nsplit][N][dstRow]
+  int dstRow;                   // mode 2: floats per destination row
+  int cbF4;                     // float4 per codebook slot (K for d % 4 == 0 pieces, K/4 for d == 1 scalars)
   int NT;                     // positions per CTA = MMA N (multiple of 16, <= 256)
   int NPOS;                   // staged positions per plane (NT + halo)
   int planeF4;                // float4 per staged plane set (one of hi / lo, one buffer)
@@ -154,6 +159,8 @@ struct qcnn_layer {
   // FC scratch
   float* d_partial;
   size_t partial_bytes;
+  float* d_flat;         // tensor-core FC path: source gathered into [N][Din] (NHWC-mapped sources only)
+  size_t flat_bytes;
   // tuning overrides (0 = automatic)
   int opt_fc_nsplit;
   int opt_fc_tn;
@@ -170,6 +177,9 @@ void PlanConvDec(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvP
 int LaunchConvDec(const ConvPlan& p, const ConvArgs& a, cudaStream_t st);
 // pq_gemm_tc.cu
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
+size_t PqGemmSmemBytes(const GemmArgs& a);
+int LaunchPqGemmArgs(const GemmArgs& a, long long blocks, cudaStream_t st);
+int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st, bool* handled);
 int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st);
 
 int LaunchRelu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, cudaStream_t st);

@@ -73,6 +73,58 @@ def test_fc_parity(case, po, qcnn, ctx):
     layer.close()
 
 
+FC_TC_CASES = [
+    # large batches take the tensor-core path (decode-at-use GEMM, split-K): (N, Din, Dout, S, K, d)
+    (128, 512, 200, 128, 32, 4),
+    (200, 4096, 1000, 4096, 16, 1),   # fc8-like: scalar codewords, Dout not a multiple of 16
+    (300, 1024, 520, 128, 64, 8),     # two batch tiles, d = 8
+    (256, 2048, 4096, 512, 32, 4),    # fc7-like
+    (100, 304, 96, 38, 128, 8),       # odd k-step count (Din/8 = 38)
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FC_TC_CASES)
+def test_fc_tc_parity(case, po, qcnn, ctx):
+    import torch
+    N, Din, Dout, S, K, d = case
+    rng = np.random.RandomState(hash(case) % (2 ** 31))
+    ctrd = (rng.randn(S, K, d) * 0.05).astype(np.float32)
+    asmt = rng.randint(0, K, size=(Dout, S)).astype(np.uint8)
+    bias = (rng.randn(Dout) * 0.1).astype(np.float32)
+    x = rand_act(rng, (N, Din))
+    ref = po.fc_aprx(x, ctrd, asmt, bias)
+    layer = qcnn.FcLayer(ctx, Din, ctrd, asmt, bias)
+    xd = torch.from_numpy(x).cuda()
+    y = layer.forward(xd).cpu().numpy()
+    assert close(y, ref) <= RTOL, close(y, ref)
+    yr = layer.forward(xd, relu=True).cpu().numpy()
+    assert close(yr, np.maximum(ref, 0)) <= RTOL
+    # explicit single split keeps the gather kernel and the reference's accumulation order: bit-exact
+    layer.set_param("fc_nsplit", 1)
+    assert np.array_equal(layer.forward(xd).cpu().numpy(), ref)
+    layer.close()
+
+
+@pytest.mark.gpu
+def test_fc_tc_nhwc_source(po, qcnn, ctx):
+    import torch
+    rng = np.random.RandomState(11)
+    N, H, W, Cc, Dout, K, d = 130, 6, 6, 32, 256, 32, 4
+    Din = H * W * Cc
+    S = Din // d
+    ctrd = (rng.randn(S, K, d) * 0.05).astype(np.float32)
+    asmt = rng.randint(0, K, size=(Dout, S)).astype(np.uint8)
+    bias = (rng.randn(Dout) * 0.1).astype(np.float32)
+    x = rand_act(rng, (N, H, W, Cc))
+    ref = po.fc_aprx(po.nhwc_to_nchw(x).reshape(N, -1), ctrd, asmt, bias)
+    layer = qcnn.FcLayer(ctx, Din, ctrd, asmt, bias)
+    layer.set_src_nhwc(H, W, Cc)
+    y = layer.forward(torch.from_numpy(x).cuda().view(N, -1)).cpu().numpy()
+    assert close(y, ref) <= RTOL, close(y, ref)
+    layer.close()
+
+
 @pytest.mark.gpu
 def test_fc_nhwc_source_fold(po, qcnn, ctx):
     """fc6-style: the NHWC->NCHW permute of the reference (CaffeEva.cc:236-238) folded into the LUT addressing."""

@@ -47,7 +47,9 @@ constexpr int kIssuer = 128;     // first lane of warp 4
 constexpr int kStagers = 96;     // warps 5-7
 constexpr int kStager0 = 160;
 constexpr int kMaxSlots = 5;
-constexpr int kCbBufs = 3;      // codebook / index buffers: the decoders run ahead of the position planes
+constexpr int kMaxGT = 8;        // k-steps per stage (TMEM ring: NSLOT * GT * 16 columns <= 256)
+constexpr int kRegPos = 16;     // float4 a stager thread holds in registers (convolution modes: planeF4 <= 16 * 96)
+constexpr int kCbBufs = 4;      // codebook / index buffers: the decoders run ahead of the position planes
 
 __device__ __forceinline__ uint32_t SmemU32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void CpAsync16(void* smemDst, const void* gsrc, bool valid) {
@@ -79,6 +81,12 @@ __device__ __forceinline__ void MbarWait(uint64_t* mbar, uint32_t parity) {
 __device__ __forceinline__ void UmmaCommit(uint64_t* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemU32(mbar)) : "memory");
 }
+// one lane of the (converged) warp
+__device__ __forceinline__ bool ElectOne() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[tmem] * B[smem descriptor]
 __device__ __forceinline__ void UmmaTf32Ts(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -92,6 +100,21 @@ __device__ __forceinline__ void SplitTf32x4(const float4 v, float4& hi, float4& 
   hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
 }
 
+// one k-step of decoded weights (two 4-float halves) -> hi | lo -> 16 TMEM columns of this thread's lane
+__device__ __forceinline__ void StoreWeights(uint32_t taddr, const float4 w0, const float4 w1) {
+  float4 h0, l0, h1, l1;
+  SplitTf32x4(w0, h0, l0);
+  SplitTf32x4(w1, h1, l1);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               :: "r"(taddr),
+                  "r"(__float_as_uint(h0.x)), "r"(__float_as_uint(h0.y)), "r"(__float_as_uint(h0.z)), "r"(__float_as_uint(h0.w)),
+                  "r"(__float_as_uint(h1.x)), "r"(__float_as_uint(h1.y)), "r"(__float_as_uint(h1.z)), "r"(__float_as_uint(h1.w)),
+                  "r"(__float_as_uint(l0.x)), "r"(__float_as_uint(l0.y)), "r"(__float_as_uint(l0.z)), "r"(__float_as_uint(l0.w)),
+                  "r"(__float_as_uint(l1.x)), "r"(__float_as_uint(l1.y)), "r"(__float_as_uint(l1.z)), "r"(__float_as_uint(l1.w))
+               : "memory");
+}
+
 struct SmemMap {  // byte offsets inside the dynamic shared memory
   int planes, raw, cbs, ids, tab, posoff, posrow, outoff, bias, bars, tmem, total;
 };
@@ -99,7 +122,7 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   SmemMap m;
   int o = 0;
   m.planes = o; o += 2 * 2 * a.planeF4 * 16;            // [buf][hi,lo][planeF4]
-  m.raw = o;    o += a.planeF4 * 16;                    // cp.async target of the positions
+  m.raw = o;    o += a.mode == 2 ? 2 * a.planeF4 * 16 : 0;   // mode 2: [2] cp.async targets of the positions (two chunks in flight)
   m.cbs = o;    o += kCbBufs * a.cbSlots * a.cbF4 * 16; // [cbuf][slot][cbF4] codeword pieces (raw fp32)
   m.ids = o;    o += kCbBufs * a.idRows * 128;          // [cbuf][row][128 channels] assignment indices
   m.tab = o;    o += a.ntab * 16;
@@ -120,7 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   const int K = a.K, NT = a.NT, GT = a.GT, NSLOT = a.NSLOT;
 
   float4* planes = reinterpret_cast<float4*>(smem + sm.planes);
-  float4* raw = reinterpret_cast<float4*>(smem + sm.raw);
+  float4* rawAll = reinterpret_cast<float4*>(smem + sm.raw);
+  float4* raw = rawAll;
   float4* cbs = reinterpret_cast<float4*>(smem + sm.cbs);
   uint8_t* ids = smem + sm.ids;
   KStep* tabS = reinterpret_cast<KStep*>(smem + sm.tab);
@@ -176,7 +200,6 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       const bool colOk = i < a.N && wi >= 0 && wi < a.Wi;
       off = static_cast<int>((i - i0) * a.srcImg) + (r * a.stride - a.pad) * a.rowStride + wi * a.colStride;
       posrow[p] = colOk ? r * a.stride - a.pad : -(1 << 28);
-      raw[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // components beyond Cg stay zero
     } else {
       // float4 p = ((k-step i, half), image n): features [8i + 4 half, +4) of the chunk, image Q0 + n
       const int n = p % NT, ih = p / NT;
@@ -213,12 +236,15 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   const uint32_t tmemD = *tmemBase;          // D: columns [0, NT)
   const uint32_t tmemA = tmemD + 256;        // A ring: columns [256, 256 + NSLOT*GT*16)
 
-  if (warp >= 5) {
+  const int warpU = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform role selector
+  if (warpU >= 5) {
     // =========================== stagers ===========================
     const int st = tid - kStager0;
     // chunk kc: positions (raw) + codebook slices + index rows, all by cp.async (one group)
     auto fetchChunk = [&](int kc) {
       const int cbuf = kc % kCbBufs;
+      float4* raw = rawAll + (kc & 1) * a.planeF4;
+      (void)raw;
       if (a.mode == 0) {
         // per-chunk scalars: the two 4-channel halves, their subspaces and the offsets inside the codewords
         const int taps = a.ksz * a.ksz;
@@ -226,15 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         const bool okA = chA < a.Cg, okB = chB < a.Cg;
         const int sA = okA ? chA / a.d : 0, jA = okA ? chA - sA * a.d : 0;
         const int sB = okB ? chB / a.d : 0, jB = okB ? chB - sB * a.d : 0;
-        // positions: float4 p = (half, pos): channels [kc*8 + half*4, +4) of the group
-        const float* srcG = srcBase + g * a.Cg + chA;
-#pragma unroll 2
-        for (int p = st; p < a.planeF4; p += kStagers) {
-          const int off = posoff[p];
-          const bool hb = p >= a.NPOS;
-          const bool ok = off >= 0 && (hb ? okB : okA);
-          CpAsync16(raw + p, srcG + (ok ? off + (hb ? 4 : 0) : 0), ok);
-        }
+        // (positions travel through registers: loadPos / storePos)
         // codebook slices: slot = half
         const float* cA = a.ctrd + static_cast<size_t>(sA) * K * a.d + jA;
         const float* cB = a.ctrd + static_cast<size_t>(sB) * K * a.d + jB;
@@ -259,14 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       if (a.mode == 1) {
         // chunk = phase row ph: pixels of input rows r*stride + ph - pad, one 4-byte copy per channel
         const int ph = kc;
-        const float* srcG = srcBase + static_cast<size_t>(g) * a.Cg * a.chStride + ph * a.rowStride;
-#pragma unroll 2
-        for (int p = st; p < a.planeF4; p += kStagers) {
-          const bool ok = static_cast<unsigned>(posrow[p] + ph) < static_cast<unsigned>(a.Hi);
-          const float* px = srcG + (ok ? posoff[p] : 0);
-          float* dstp = reinterpret_cast<float*>(raw + p);
-          for (int ch = 0; ch < a.Cg; ch++) CpAsync4(dstp + ch, px + ch * a.chStride, ok);
-        }
+        // (positions travel through registers: loadPos / storePos)
         // codebook: slot 0 = the first 4 floats of every codeword of subspace 0, slot 1 = zeros (unpaired taps)
         float4* cdst = cbs + cbuf * a.cbSlots * K;
         for (int k = st; k < K; k += kStagers) {
@@ -328,12 +339,71 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       }
       CpAsyncCommit();
     };
+    // Positions of the convolution modes: global -> registers -> hi/lo planes.  (16-byte cp.async of scattered pieces
+    // costs one shared-memory wavefront per THREAD -- profiles/r01_pq_gemm_staging.md -- whereas a 128-bit store of 32
+    // consecutive float4 costs four per warp.)  A thread owns float4 st, st+96, ...: at most kRegPos of them.
+    float4 rg[kRegPos];
+    int poffR[kRegPos];        // chunk-invariant source offset of the thread's float4 (mode 0: incl. the half's +4)
+    int prowR[kRegPos];        // mode 1: first input row (phase row 0), very negative when the column is outside
+    uint32_t pvalid = 0;       // mode 0: bit i = the float4 exists and its position is inside an image
+    uint32_t phalf = 0;        // mode 0: bit i = second half (channels 4..7 of the chunk)
+    if (a.mode != 2) {
+#pragma unroll
+      for (int i = 0; i < kRegPos; i++) {
+        const int p = st + i * kStagers;
+        poffR[i] = 0; prowR[i] = -(1 << 28);
+        if (p < a.planeF4) {
+          const int off = posoff[p];
+          if (a.mode == 0) {
+            const bool hb = p >= a.NPOS;
+            poffR[i] = off + (hb ? 4 : 0);
+            if (off >= 0) pvalid |= 1u << i;
+            if (hb) phalf |= 1u << i;
+          } else {
+            poffR[i] = off;
+            prowR[i] = posrow[p];
+          }
+        }
+      }
+    }
+    auto loadPos = [&](int kc) {
+      if (a.mode == 0) {
+        const int chA = kc * 8;
+        uint32_t m = pvalid;
+        if (chA >= a.Cg) m = 0;
+        else if (chA + 4 >= a.Cg) m &= ~phalf;
+        const float* srcG = srcBase + g * a.Cg + chA;
+#pragma unroll
+        for (int i = 0; i < kRegPos; i++) {
+          rg[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if ((m >> i) & 1u) rg[i] = __ldg(reinterpret_cast<const float4*>(srcG + poffR[i]));
+        }
+      } else {
+        const int ph = kc;
+        const float* srcG = srcBase + static_cast<size_t>(g) * a.Cg * a.chStride + ph * a.rowStride;
+#pragma unroll
+        for (int i = 0; i < kRegPos; i++) {
+          rg[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (static_cast<unsigned>(prowR[i] + ph) < static_cast<unsigned>(a.Hi)) {
+            const float* px = srcG + poffR[i];
+            rg[i].x = __ldg(px);
+            if (a.Cg > 1) rg[i].y = __ldg(px + a.chStride);
+            if (a.Cg > 2) rg[i].z = __ldg(px + 2 * a.chStride);
+            if (a.Cg > 3) rg[i].w = __ldg(px + 3 * a.chStride);
+          }
+        }
+      }
+    };
+    const bool regPos = a.mode != 2;
     fetchChunk(0);
+    if (regPos) loadPos(0);
+    if (nChunks > 1) fetchChunk(1);
     long long sCp = 0, sEB = 0, sEC = 0, sT0 = clock64();
     for (int kc = 0; kc < nChunks; kc++) {
       const int buf = kc & 1;
       long long c0 = clock64();
-      CpAsyncWaitAll();
+      if (kc + 1 < nChunks) asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk kc landed, kc+1 may be in flight
+      else CpAsyncWaitAll();
       asm volatile("bar.sync 1, 96;" ::: "memory");     // every stager's copies of chunk kc have landed
       sCp += clock64() - c0;
       MbarArrive(fullC + kc % kCbBufs);                  // the decoders may start on chunk kc
@@ -342,21 +412,38 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       sEB += clock64() - c0;
       float4* pHi = planes + (buf * 2 + 0) * a.planeF4;
       float4* pLo = planes + (buf * 2 + 1) * a.planeF4;
-      for (int p = st; p < a.planeF4; p += kStagers) {
-        float4 hi, lo;
-        SplitTf32x4(raw[p], hi, lo);
-        pHi[p] = hi;
-        pLo[p] = lo;
+      if (regPos && (a.dbgSkip & 2) && kc >= 2) {
+      } else if (regPos) {
+#pragma unroll
+        for (int i = 0; i < kRegPos; i++) {
+          const int p = st + i * kStagers;
+          if (p < a.planeF4) {
+            float4 hi, lo;
+            SplitTf32x4(rg[i], hi, lo);
+            pHi[p] = hi;
+            pLo[p] = lo;
+          }
+        }
+      } else {
+        const float4* rawK = rawAll + buf * a.planeF4;
+#pragma unroll 2
+        for (int p = st; p < a.planeF4; p += kStagers) {
+          float4 hi, lo;
+          SplitTf32x4(rawK[p], hi, lo);
+          pHi[p] = hi;
+          pLo[p] = lo;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // planes are read by the tensor core
       MbarArrive(fullB + buf);
-      asm volatile("bar.sync 1, 96;" ::: "memory");     // raw may be overwritten
-      if (kc + 1 < nChunks) {
-        const int nb = (kc + 1) % kCbBufs;
+      if (regPos) { if (kc + 1 < nChunks && !((a.dbgSkip & 2) && kc >= 1)) loadPos(kc + 1); }
+      else asm volatile("bar.sync 1, 96;" ::: "memory");     // this raw buffer may be overwritten
+      if (kc + 2 < nChunks) {
+        const int nb = (kc + 2) % kCbBufs;
         c0 = clock64();
-        if (kc + 1 >= kCbBufs) MbarWait(emptyC + nb, (((kc + 1) / kCbBufs) - 1) & 1);
+        if (kc + 2 >= kCbBufs) MbarWait(emptyC + nb, (((kc + 2) / kCbBufs) - 1) & 1);
         sEC += clock64() - c0;
-        fetchChunk(kc + 1);
+        if ((a.dbgSkip & 2) && regPos) CpAsyncCommit(); else fetchChunk(kc + 2);
       }
     }
     if (a.dbg && st == 0) {
@@ -365,12 +452,17 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       atomicAdd(a.dbg + 10, static_cast<unsigned long long>(sEB));
       atomicAdd(a.dbg + 11, static_cast<unsigned long long>(sEC));
     }
-  } else if (warp == 4) {
+  } else if (warpU == 4) {
     // =========================== MMA issuer ===========================
-    if (tid == kIssuer) {
+    // The whole warp runs the loop on warp-uniform values (k-step table read from the kernel parameters, i.e. the
+    // constant bank, so descriptors stay in uniform registers); one elected lane issues the tcgen05 instructions.
+    // (Issuing from a single divergent thread wraps every UTCHMMA in an elect loop plus R2UR moves: ~160 clk per MMA,
+    //  above the 128 clk the MMA itself takes -- profiles/r01_pq_gemm_issue.md.)
+    {
       // instruction descriptor: D = F32, A = B = TF32, K-major, N = NT, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) | (8u << 24);
       const uint64_t descFixed = (static_cast<uint64_t>(8) << 32) | (static_cast<uint64_t>(1) << 46);  // SBO = 128 B
+      const uint32_t planes0 = SmemU32(planes);
       int t = 0;
       uint32_t acc = 0;
       long long wBC = 0, wA = 0, tStart = clock64();
@@ -380,8 +472,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         MbarWait(fullB + buf, (kc >> 1) & 1);
         wBC += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t dHi = descFixed | ((SmemU32(planes + (buf * 2 + 0) * a.planeF4) >> 4) & 0x3FFFu);
-        const uint64_t dLo = descFixed | ((SmemU32(planes + (buf * 2 + 1) * a.planeF4) >> 4) & 0x3FFFu);
+        const uint64_t dHi = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 0) * a.planeF4) * 16u) >> 4) & 0x3FFFu);
+        const uint64_t dLo = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 1) * a.planeF4) * 16u) >> 4) & 0x3FFFu);
         const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0];
         const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kc : 0];
         for (int s0 = 0; s0 < ne; s0 += GT, t++) {
@@ -391,22 +483,29 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
           wA += clock64() - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int n = min(GT, ne - s0);
-          for (int i = 0; i < n; i++) {
-            const KStep ks = tabS[e0 + s0 + i];
-            const uint64_t off = static_cast<uint64_t>(static_cast<uint32_t>(ks.bStart)) |
-                                 (static_cast<uint64_t>(static_cast<uint32_t>(ks.lbo)) << 16);
-            const uint32_t aHi = tmemA + static_cast<uint32_t>((slot * GT + i) * 16), aLo = aHi + 8;
-            UmmaTf32Ts(tmemD, aHi, dHi + off, idesc, acc);
-            UmmaTf32Ts(tmemD, aHi, dLo + off, idesc, 1u);
-            UmmaTf32Ts(tmemD, aLo, dHi + off, idesc, 1u);
-            acc = 1u;
+          if (ElectOne()) {
+            for (int i = 0; i < n; i++) {
+              const KStep ks = a.tab[e0 + s0 + i];
+              const uint64_t off = static_cast<uint64_t>(static_cast<uint32_t>(ks.bStart)) |
+                                   (static_cast<uint64_t>(static_cast<uint32_t>(ks.lbo)) << 16);
+              const uint32_t aHi = tmemA + static_cast<uint32_t>((slot * GT + i) * 16), aLo = aHi + 8;
+              UmmaTf32Ts(tmemD, aHi, dHi + off, idesc, acc);
+              UmmaTf32Ts(tmemD, aHi, dLo + off, idesc, 1u);
+              UmmaTf32Ts(tmemD, aLo, dHi + off, idesc, 1u);
+              acc = 1u;
+            }
+            // commits are issued by the thread that issued the MMAs they track
+            UmmaCommit(emptyA + slot);
+            if (s0 + GT >= ne) {
+              UmmaCommit(emptyB + buf);
+              if (kc == nChunks - 1) UmmaCommit(doneBar);
+            }
           }
-          UmmaCommit(emptyA + slot);
+          acc = 1u;
+          __syncwarp();
         }
-        UmmaCommit(emptyB + buf);
       }
-      UmmaCommit(doneBar);
-      if (a.dbg) {
+      if (a.dbg && lane == 0) {
         const long long tIssue = clock64() - tStart;
         long long c0 = clock64();
         MbarWait(doneBar, 0);
@@ -414,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         atomicAdd(a.dbg + 1, static_cast<unsigned long long>(wBC));
         atomicAdd(a.dbg + 2, static_cast<unsigned long long>(wA));
         atomicAdd(a.dbg + 3, static_cast<unsigned long long>(clock64() - c0));
-                atomicAdd(a.dbg + 5, 1ull);
+        atomicAdd(a.dbg + 5, 1ull);
       }
     }
   } else {
@@ -443,37 +542,45 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const int n = min(GT, ne - s0);
-        for (int i = 0; i < n; i++) {
-          const KStep ks = tabS[e0 + s0 + i];
-          float4 w0, w1;
-          if (a.d == 1) {
+        if (a.d == 1) {
+          for (int i = 0; i < n; i++) {
             // scalar codewords: every feature is its own subspace (rows / slots idx0 .. idx0+3 and idx1 .. idx1+3)
+            const KStep ks = tabS[e0 + s0 + i];
             const uint8_t* r0 = idb + ks.idx0 * 128;
             const uint8_t* r1 = idb + ks.idx1 * 128;
             const float* c0p = cbf + ks.cb0 * K;
             const float* c1p = cbf + ks.cb1 * K;
+            float4 w0, w1;
             w0.x = c0p[r0[0] >> a.kshift];           w0.y = c0p[K + (r0[128] >> a.kshift)];
             w0.z = c0p[2 * K + (r0[256] >> a.kshift)]; w0.w = c0p[3 * K + (r0[384] >> a.kshift)];
             w1.x = c1p[r1[0] >> a.kshift];           w1.y = c1p[K + (r1[128] >> a.kshift)];
             w1.z = c1p[2 * K + (r1[256] >> a.kshift)]; w1.w = c1p[3 * K + (r1[384] >> a.kshift)];
-          } else {
-            const int i0x = idb[ks.idx0 * 128] >> a.kshift;
-            const int i1x = idb[ks.idx1 * 128] >> a.kshift;
-            w0 = cb[ks.cb0 * K + i0x];
-            w1 = cb[ks.cb1 * K + i1x];
+            StoreWeights(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0, w1);
           }
-          float4 h0, l0, h1, l1;
-          SplitTf32x4(w0, h0, l0);
-          SplitTf32x4(w1, h1, l1);
-          const uint32_t taddr = tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16);
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-                       "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                       :: "r"(taddr),
-                          "r"(__float_as_uint(h0.x)), "r"(__float_as_uint(h0.y)), "r"(__float_as_uint(h0.z)), "r"(__float_as_uint(h0.w)),
-                          "r"(__float_as_uint(h1.x)), "r"(__float_as_uint(h1.y)), "r"(__float_as_uint(h1.z)), "r"(__float_as_uint(h1.w)),
-                          "r"(__float_as_uint(l0.x)), "r"(__float_as_uint(l0.y)), "r"(__float_as_uint(l0.z)), "r"(__float_as_uint(l0.w)),
-                          "r"(__float_as_uint(l1.x)), "r"(__float_as_uint(l1.y)), "r"(__float_as_uint(l1.z)), "r"(__float_as_uint(l1.w))
-                       : "memory");
+        } else {
+          // the stage's k-steps are independent: table entries, index bytes and codeword pieces of all of them are in
+          // flight together (one decoder warp per SM sub-partition: latency, not bandwidth, paces this role)
+          int i0x[kMaxGT], i1x[kMaxGT];
+#pragma unroll
+          for (int i = 0; i < kMaxGT; i++) {
+            if (i < n && !(a.dbgSkip & 1)) {
+              const KStep ks = tabS[e0 + s0 + i];
+              i0x[i] = ks.cb0 * K + (idb[ks.idx0 * 128] >> a.kshift);
+              i1x[i] = ks.cb1 * K + (idb[ks.idx1 * 128] >> a.kshift);
+            }
+          }
+          float4 w0[kMaxGT], w1[kMaxGT];
+#pragma unroll
+          for (int i = 0; i < kMaxGT; i++) {
+            if (i < n) {
+              if (a.dbgSkip & 1) { w0[i] = make_float4(1.0f, 2.0f, 3.0f, 4.0f); w1[i] = w0[i]; }
+              else { w0[i] = cb[i0x[i]]; w1[i] = cb[i1x[i]]; }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kMaxGT; i++) {
+            if (i < n) StoreWeights(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0[i], w1[i]);
+          }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -556,6 +663,7 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
         ga.PW = PWp; ga.IB = IB; ga.NT = NT; ga.GT = GT; ga.NSLOT = std::min(kMaxSlots, 16 / GT);
         ga.NPOS = RoundUp(NT + ((L->ksz - 1) / st) * (PWp + 1), 8);
         ga.planeF4 = st * ga.NPOS;
+        if (ga.planeF4 > kRegPos * kStagers) continue;
         ga.cbSlots = 2; ga.idRows = rowsPer * L->ksz;
         ga.nChunks = st;
         ga.K = L->K; ga.cbF4 = L->K;
@@ -610,6 +718,7 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
       ga.NPOS = RoundUp(NT + (L->ksz - 1) * (PW + 1), 8);
       if (ga.NPOS > 16000) continue;
       ga.planeF4 = 2 * ga.NPOS;
+      if (ga.planeF4 > kRegPos * kStagers) continue;
       ga.cbSlots = 2; ga.idRows = 2 * taps;
       ga.nChunks = CeilDiv(Cg, 8);
       ga.ntab = taps;
@@ -650,6 +759,8 @@ int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N
   QCNN_CHECK(blocks <= 2147483647LL, "qcnn_conv_aprx_forward: batch too large for the tensor-core tiling");
   QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   static const bool dbg = getenv("QCNN_GEMM_DBG") != nullptr;
+  static const int skip = getenv("QCNN_GEMM_SKIP") ? atoi(getenv("QCNN_GEMM_SKIP")) : 0;
+  a.dbgSkip = skip;
   if (dbg) {
     QCNN_CUDA(cudaMalloc(&a.dbg, 128));
     QCNN_CUDA(cudaMemsetAsync(a.dbg, 0, 128, st));

@@ -101,6 +101,7 @@ struct GemmArgs {
   const uint8_t* asmt;
   const float* bias;
   unsigned long long* dbg;    // optional cycle counters of the MMA issuer (QCNN_GEMM_DBG=1)
+  int dbgSkip;                // timing experiments only (QCNN_GEMM_SKIP): 1 decoders skip their loads, 2 stagers skip their work
   long long srcImg, dstImg;   // elements per source / destination image
   int N, Hi, Wi, Cin, Ho, Wo, Cout, ksz, pad, stride, G, Cg, Kg, KgPad, S, K, d;
   int mode;                   // 0 stride-1 conv, 1 strided conv on phase planes, 2 fully connected

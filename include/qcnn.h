@@ -73,7 +73,9 @@ QCNN_API int qcnn_fc_layer_set_src_nhwc(qcnn_layer* layer, int H, int W, int C);
 /* Conv only: the source is NCHW [N][C][H][W] (the API input of CaffeEva::ExecForwardPass, CaffeEva.cc:225-228). */
 QCNN_API int qcnn_conv_layer_set_src_nchw(qcnn_layer* layer, int enable);
 /* tuning overrides for tests/benchmarks: "fc_nsplit" (subspace splits, 0 = automatic; 1 reproduces the reference's
- * accumulation order exactly), "fc_tn" (images per CTA: 1, 4 or 8; 0 = automatic) */
+ * accumulation order exactly), "fc_tn" (images per CTA: 1, 4 or 8; 0 = automatic), "tensor_core" (1 = default: large
+ * batches may run as decode-at-use GEMMs on the tensor cores, 3xTF32; 0 = LUT + gather kernels only, the fp32
+ * strict-parity path -- tolerances of both in DESIGN.md) */
 QCNN_API int qcnn_layer_set_param(qcnn_layer* layer, const char* name, int value);
 /* one-line description of the kernel + tiling chosen for batch N */
 QCNN_API int qcnn_layer_describe(qcnn_layer* layer, int N, char* buf, size_t cap);

@@ -1278,8 +1278,10 @@ int PlanConv(qcnn_layer* L, int N) {
   // decode-at-use implicit GEMM on the tensor cores (conv_dec_tc.cu)
   {
     const size_t before = cands.size();
-    PlanConvDec(L, N, &cands);
-    PlanPqGemm(L, N, &cands);
+    if (!L->opt_no_tc) {
+      PlanConvDec(L, N, &cands);
+      PlanPqGemm(L, N, &cands);
+    }
     found = found || cands.size() > before;
   }
   QCNN_CHECK(found, "qcnn_conv_layer_create: no tiling fits (Cout/grp=%d must be a multiple of 16; K=%d must be a "

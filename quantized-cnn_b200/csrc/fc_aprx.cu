@@ -289,7 +289,7 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   static const char* env = getenv("QCNN_FC_TC");
   if (env && env[0] == '0') return 0;
   if (!(env && env[0] == '1') && N < 96) return 0;
-  if (L->opt_fc_nsplit || L->opt_fc_tn) return 0;   // explicit gather-kernel tuning (fc_nsplit = 1: bit-exact reference order)
+  if (L->opt_fc_nsplit || L->opt_fc_tn || L->opt_no_tc) return 0;   // explicit gather-kernel tuning (fc_nsplit = 1: bit-exact reference order)
   if (L->Din % 8 != 0 || !(L->d == 1 || L->d % 4 == 0) || L->S * L->d < L->Din || L->K > 256 || L->K % 4 != 0) return 0;
   qcnn_ctx* ctx = L->ctx;
   const float* x = src;

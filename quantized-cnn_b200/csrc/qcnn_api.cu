@@ -231,6 +231,13 @@ int qcnn_layer_set_param(qcnn_layer* L, const char* name, int value) {
   QCNN_CHECK(L && name, "qcnn_layer_set_param: NULL argument");
   if (!strcmp(name, "fc_nsplit")) L->opt_fc_nsplit = value;
   else if (!strcmp(name, "fc_tn")) L->opt_fc_tn = value;
+  else if (!strcmp(name, "tensor_core")) {
+    // 0: LUT + gather kernels only (fp32 adds in the reference's association; the strict-parity path);
+    // 1 (default): large batches may use the decode-at-use tensor-core GEMMs (3xTF32, wider tolerance: DESIGN.md)
+    L->opt_no_tc = value ? 0 : 1;
+    L->plan_N = 0; L->tuned = 0;
+    if (L->tunedPlans) L->tunedPlans->clear();
+  }
   else { SetError("qcnn_layer_set_param: unknown parameter '%s'", name); return 1; }
   return 0;
 }

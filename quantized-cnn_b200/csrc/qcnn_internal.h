@@ -165,6 +165,7 @@ struct qcnn_layer {
   // tuning overrides (0 = automatic)
   int opt_fc_nsplit;
   int opt_fc_tn;
+  int opt_no_tc;         // 1: never use the decode-at-use tensor-core kernels for this layer
 };
 
 namespace qcnn {

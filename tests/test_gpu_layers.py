@@ -13,6 +13,9 @@ import numpy as np
 import pytest
 
 RTOL = 1e-4
+# decode-at-use tensor-core kernels (3xTF32, fp32 accumulation inside the tensor core over all k-steps): measured
+# <= 1e-4 per layer on the AlexNet shapes (tools/accuracy.py); the LUT + gather kernels stay within RTOL (measured 5e-6)
+RTOL_TC = 3e-4
 
 
 def close(gpu, ref, rtol=RTOL):
@@ -97,9 +100,9 @@ def test_fc_tc_parity(case, po, qcnn, ctx):
     layer = qcnn.FcLayer(ctx, Din, ctrd, asmt, bias)
     xd = torch.from_numpy(x).cuda()
     y = layer.forward(xd).cpu().numpy()
-    assert close(y, ref) <= RTOL, close(y, ref)
+    assert close(y, ref) <= RTOL_TC, close(y, ref)
     yr = layer.forward(xd, relu=True).cpu().numpy()
-    assert close(yr, np.maximum(ref, 0)) <= RTOL
+    assert close(yr, np.maximum(ref, 0)) <= RTOL_TC
     # explicit single split keeps the gather kernel and the reference's accumulation order: bit-exact
     layer.set_param("fc_nsplit", 1)
     assert np.array_equal(layer.forward(xd).cpu().numpy(), ref)
@@ -120,6 +123,9 @@ def test_fc_tc_nhwc_source(po, qcnn, ctx):
     ref = po.fc_aprx(po.nhwc_to_nchw(x).reshape(N, -1), ctrd, asmt, bias)
     layer = qcnn.FcLayer(ctx, Din, ctrd, asmt, bias)
     layer.set_src_nhwc(H, W, Cc)
+    y = layer.forward(torch.from_numpy(x).cuda().view(N, -1)).cpu().numpy()
+    assert close(y, ref) <= RTOL_TC, close(y, ref)
+    layer.set_param("tensor_core", 0)
     y = layer.forward(torch.from_numpy(x).cuda().view(N, -1)).cpu().numpy()
     assert close(y, ref) <= RTOL, close(y, ref)
     layer.close()
@@ -184,12 +190,22 @@ def test_conv_parity(case, po, qcnn, ctx):
     got = layer.read_asmt(asmt.size).reshape(k, k, S, Cout)
     assert np.array_equal(got, np.transpose(asmt, (1, 2, 3, 0)))  # reference asmtBuf order (CaffeEva.cc:585-586)
     xd = torch.from_numpy(x).cuda()
+    # (a) default: the autotuner may pick a decode-at-use tensor-core kernel
     y = layer.forward(xd).cpu().numpy()
     assert y.shape == ref.shape
+    assert close(y, ref) <= RTOL_TC, close(y, ref)
+    if stride > 1:
+        layer.set_src_nchw(True)
+        yn = layer.forward(torch.from_numpy(po.nhwc_to_nchw(x)).cuda()).cpu().numpy()
+        assert close(yn, ref) <= RTOL_TC, close(yn, ref)
+        layer.set_src_nchw(False)
+    # (b) strict parity: LUT + gather kernels only (fp32 adds)
+    layer.set_param("tensor_core", 0)
+    y = layer.forward(xd).cpu().numpy()
     assert close(y, ref) <= RTOL, close(y, ref)
     yr = layer.forward(xd, relu=True).cpu().numpy()
     assert close(yr, np.maximum(ref, 0)) <= RTOL
-    # batch invariance: image 0 alone gives the same bits as image 0 inside the batch
+    # batch invariance: image 0 alone gives the same result as image 0 inside the batch (tilings differ per batch size)
     y0 = layer.forward(xd[:1].contiguous()).cpu().numpy()
     assert close(y0[0], y[0]) <= RTOL
     if stride > 1:

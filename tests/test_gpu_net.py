@@ -1,14 +1,28 @@
 """Whole-network parity of the device executor (C ABI: qcnn_net_*) against the CPU oracle / compiled reference.
 
-Tolerances: feature maps and logits as in test_gpu_layers (RTOL 1e-4 with tensor-magnitude scaling), softmax
-probabilities 2e-5 absolute (logit error e amplifies to p*e relative), identical top-5 ordering wherever the
-reference's own top-5 probabilities are separated by more than that."""
+Two configurations, each with its stated tolerance (metric of test_gpu_layers.close: error relative to
+max(1, |ref|, 0.1 max|ref|)):
+  strict   tensor_core = 0 on every PQ layer: LUT + gather kernels, fp32 adds.  Feature maps / logits RTOL = 1e-4
+           (measured 1.6e-5 through all 23 layers), softmax probabilities 2e-5 absolute (measured 9e-6).
+  default  the autotuner may run any layer as a decode-at-use GEMM on the tensor cores (3xTF32, accumulation inside the
+           tensor core).  Feature maps / logits 5e-4 (measured 2e-4 chained), probabilities 2e-4 absolute (measured 5e-5).
+Identical top-5 ordering wherever the reference's own top-5 probabilities are separated by more than the tolerance."""
 import os
 
 import numpy as np
 import pytest
 
 from test_gpu_layers import RTOL, close
+
+MODES = {"strict": (RTOL, 2e-5), "default": (5e-4, 2e-4)}
+
+
+def set_mode(net, mode):
+    if mode == "strict":
+        for l in range(net.layer_count):
+            pl = net.pq_layer(l)
+            if pl is not None:
+                pl.set_param("tensor_core", 0)
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -32,12 +46,15 @@ def synth_dir(po, tmp_path_factory):
 
 
 @pytest.mark.gpu
-def test_alexnet_synthetic_weights_all_feature_maps(po, qcnn, ctx, synth_dir):
+@pytest.mark.parametrize("mode", ["strict", "default"])
+def test_alexnet_synthetic_weights_all_feature_maps(po, qcnn, ctx, synth_dir, mode):
     import torch
     d, params = synth_dir
     layers = po.alexnet_layers()
     net = qcnn.Net(ctx, d, "synth", "AlexNet")
     assert net.layer_count == 23 and net.out_len == 1000
+    set_mode(net, mode)
+    RT, PT = MODES[mode]
     N = 3
     img = po.lcg_images(N, 4242)
     ref_prob, ref_maps = po.net_forward(layers, params, img, keep=True)
@@ -51,21 +68,21 @@ def test_alexnet_synthetic_weights_all_feature_maps(po, qcnn, ctx, synth_dir):
         fm = net.featmap(l, N)
         assert fm is not None, l
         e = close(fm.cpu().numpy().reshape(-1), ref_maps[l].reshape(-1))
-        assert e <= RTOL, (l, e)
-    assert close(logits.cpu().numpy(), ref_maps[22]) <= RTOL
-    assert np.abs(prob - ref_prob).max() <= 2e-5
+        assert e <= RT, (l, e)
+    assert close(logits.cpu().numpy(), ref_maps[22]) <= RT
+    assert np.abs(prob - ref_prob).max() <= PT
     # (b) fused production path gives the same answer
     net.set_keep_maps(False)
     prob_f = net.forward(imgd, logits=logits).cpu().numpy()
-    assert close(logits.cpu().numpy(), ref_maps[22]) <= RTOL
-    assert np.abs(prob_f - ref_prob).max() <= 2e-5
+    assert close(logits.cpu().numpy(), ref_maps[22]) <= RT
+    assert np.abs(prob_f - ref_prob).max() <= PT
     assert net.launch_count() < 23          # fusion really happened
     for i in range(N):
-        assert top5_consistent(prob_f[i], ref_prob[i], po)
+        assert top5_consistent(prob_f[i], ref_prob[i], po, atol=PT)
     # (c) batch invariance: per-image results do not depend on batch composition (tilings -- hence the fp32
     #     summation order -- are chosen per batch size, so "same" means within the parity tolerance)
     p1 = net.forward(imgd[1:2].contiguous()).cpu().numpy()
-    assert np.abs(p1[0] - prob_f[1]).max() <= 2e-5
+    assert np.abs(p1[0] - prob_f[1]).max() <= PT
     # (d) host-buffer entry point (H2D + chunked pipeline + D2H) == device entry point
     net.set_chunk(2)
     ph = net.forward_host(img)
@@ -78,22 +95,25 @@ def test_alexnet_synthetic_weights_all_feature_maps(po, qcnn, ctx, synth_dir):
 
 
 @pytest.mark.gpu
-def test_alexnet_shipped_weights_vs_golden_and_live_reference(po, qcnn, ctx):
+@pytest.mark.parametrize("mode", ["strict", "default"])
+def test_alexnet_shipped_weights_vs_golden_and_live_reference(po, qcnn, ctx, mode):
     """The reference's own quantized AlexNet files, loaded unchanged through the C ABI."""
     import torch
     if not po.have_alexnet():
         pytest.skip("shipped AlexNet parameters not staged under oracle/_ref/data")
     g = np.load(os.path.join(GOLD, "alexnet_kat.npz"))
     net = qcnn.Net(ctx, po.ALEXNET_DIR, po.ALEXNET_PFX, "AlexNet")
+    set_mode(net, mode)
+    RT, PT = MODES[mode]
     img = po.lcg_images(2, 12345)
     logits = torch.empty((2, 1000), dtype=torch.float32, device="cuda")
     prob = net.forward(torch.from_numpy(img).cuda(), logits=logits).cpu().numpy()
     lg = logits.cpu().numpy()
     for i in range(2):
-        assert close(lg[i], g["logits%d" % i]) <= RTOL
-        assert np.abs(prob[i] - g["prob%d" % i]).max() <= 2e-5
-        assert np.array_equal(po.topk(prob[i], 5)[0], g["top5_%d" % i])
-    assert int(prob[0].argmax()) == 533 and abs(float(prob[0][533]) - 0.621259) < 2e-5   # SURVEY.md Appendix B KAT
+        assert close(lg[i], g["logits%d" % i]) <= RT
+        assert np.abs(prob[i] - g["prob%d" % i]).max() <= PT
+        assert top5_consistent(prob[i], g["prob%d" % i], po, atol=PT)
+    assert int(prob[0].argmax()) == 533 and abs(float(prob[0][533]) - 0.621259) < PT   # SURVEY.md Appendix B KAT
     # decoded device assignment tables are bit-identical to the reference's asmtBuf
     params = po.load_model(po.ALEXNET_DIR, po.ALEXNET_PFX, po.alexnet_layers())
     for l, p in params.items():
@@ -106,8 +126,8 @@ def test_alexnet_shipped_weights_vs_golden_and_live_reference(po, qcnn, ctx):
         pg = net.forward(torch.from_numpy(imgs).cuda()).cpu().numpy()
         for i in range(4):
             pr = ref.forward(imgs[i])
-            assert np.abs(pg[i] - pr).max() <= 2e-5
-            assert top5_consistent(pg[i], pr, po)
+            assert np.abs(pg[i] - pr).max() <= PT
+            assert top5_consistent(pg[i], pr, po, atol=PT)
         ref.close()
     net.close()
 
@@ -130,6 +150,9 @@ def test_custom_layer_table_pool_before_lrn(po, qcnn, ctx, tmp_path):
     rng = np.random.RandomState(1)
     img = (rng.randn(5, *chw) * 4).astype(np.float32)
     ref = po.net_forward(layers, params, img)
+    out = net.forward(torch.from_numpy(img).cuda()).cpu().numpy()
+    assert close(out, ref) <= MODES["default"][0]
+    set_mode(net, "strict")
     out = net.forward(torch.from_numpy(img).cuda()).cpu().numpy()
     assert close(out, ref) <= RTOL
     net.close()

@@ -4,6 +4,8 @@
 // NHWC maps, channel index fastest across lanes (coalesced), grid-stride loops sized to the SM count.
 #include "qcnn_internal.h"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -91,7 +93,10 @@ __global__ void lrn_maxpool_kernel(const float* __restrict__ src, float* __restr
 
 // 8 consecutive channels of one pixel at once: the squared/scaled window terms are computed once and shared by the
 // 8 sliding sums (same per-output operation order as LrnAt / the reference).  C % 4 == 0, c0 % 8 == 0.
-template <int SIZE>
+// FAST075: beta == 0.75 (every layer table of the reference, CaffePara.cc:31,35,...): sum^-0.75 = r * sqrt(r) with
+// r = rsqrt(sum) -- within ~3 ulp of the reference's expf(-0.75 * logf(sum)) (itself ~4 ulp from the true value; the
+// LRN parity tolerance is 1e-5) at a fifth of the instructions, which is what bounds this kernel.
+template <int SIZE, bool FAST075>
 __device__ __forceinline__ void LrnChunk8(const float* __restrict__ px, int c0, int C, float coeff, float kini,
                                           float nbeta, float (&out)[8]) {
   constexpr int RAD = (SIZE - 1) / 2;
@@ -116,20 +121,26 @@ __device__ __forceinline__ void LrnChunk8(const float* __restrict__ px, int c0, 
     float sum = kini;
 #pragma unroll
     for (int w = 0; w < SIZE; w++) sum = __fadd_rn(sum, t[c + w]);
-    out[c] = __fmul_rn(x[LO + c], expf(__fmul_rn(nbeta, logf(sum))));
+    if (FAST075) {
+      const float r = rsqrtf(sum);
+      out[c] = __fmul_rn(x[LO + c], __fmul_rn(r, __fsqrt_rn(r)));
+    } else {
+      out[c] = __fmul_rn(x[LO + c], expf(__fmul_rn(nbeta, logf(sum))));
+    }
   }
 }
 
-// Tiled variant: one CTA per (image, output row).  The <= ksz input rows the row needs are normalised ONCE into
-// shared memory and then pooled, so the expf/logf pair runs ~ksz/stride times per input element instead of
-// ksz^2/stride^2 times, and the normalised map still never reaches HBM.
-template <int SIZE>
+// Tiled variant: one CTA per (image, `ro` output rows).  The input rows those output rows need are normalised ONCE
+// into shared memory and then pooled, so the power function runs ~((ro-1)*stride+ksz)/(ro*stride) times per input element
+// instead of ksz^2/stride^2 times, and the normalised map still never reaches HBM.
+template <int SIZE, bool FAST075>
 __global__ void lrn_maxpool_tiled_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int C,
                                          int Ho, int Wo, int size, float coeff, float kini, float nbeta, int ksz,
-                                         int pad, int stride) {
+                                         int pad, int stride, int ro) {
   extern __shared__ float tile[];  // [rows][W][C]
-  const int ho = blockIdx.x, n = blockIdx.y;
-  const int hL = max(0, ho * stride - pad), hU = min(H, ho * stride + ksz - pad) - 1;
+  const int ho0 = blockIdx.x * ro, n = blockIdx.y;
+  const int hoN = min(Ho, ho0 + ro);
+  const int hL = max(0, ho0 * stride - pad), hU = min(H, (hoN - 1) * stride + ksz - pad) - 1;
   const int rows = hU - hL + 1;
   const int rowLen = W * C;
   const float* base = src + (static_cast<size_t>(n) * H + hL) * rowLen;
@@ -138,7 +149,7 @@ __global__ void lrn_maxpool_tiled_kernel(const float* __restrict__ src, float* _
     for (int e = threadIdx.x; e < rows * W * cpp; e += blockDim.x) {
       const int p = e / cpp, c0 = (e - p * cpp) << 3;
       float o[8];
-      LrnChunk8<(SIZE > 0 ? SIZE : 1)>(base + static_cast<size_t>(p) * C, c0, C, coeff, kini, nbeta, o);
+      LrnChunk8<(SIZE > 0 ? SIZE : 1), FAST075>(base + static_cast<size_t>(p) * C, c0, C, coeff, kini, nbeta, o);
       float4* tp = reinterpret_cast<float4*>(tile + static_cast<size_t>(p) * C + c0);
       tp[0] = make_float4(o[0], o[1], o[2], o[3]);
       tp[1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -151,12 +162,16 @@ __global__ void lrn_maxpool_tiled_kernel(const float* __restrict__ src, float* _
     }
   }
   __syncthreads();
-  float* out = dst + (static_cast<size_t>(n) * Ho + ho) * Wo * C;
-  for (int e = threadIdx.x; e < Wo * C; e += blockDim.x) {
-    const int wo = e / C, c = e - wo * C;
+  const int rowOut = Wo * C;
+  float* out = dst + (static_cast<size_t>(n) * Ho + ho0) * rowOut;
+  for (int e = threadIdx.x; e < (hoN - ho0) * rowOut; e += blockDim.x) {
+    const int r0 = e / rowOut, rem = e - r0 * rowOut;
+    const int wo = rem / C, c = rem - wo * C;
+    const int ho = ho0 + r0;
+    const int rL = max(0, ho * stride - pad) - hL, rU = min(H, ho * stride + ksz - pad) - 1 - hL;
     const int wL = max(0, wo * stride - pad), wU = min(W, wo * stride + ksz - pad) - 1;
     float m = -INFINITY;
-    for (int r = 0; r < rows; r++)
+    for (int r = rL; r <= rU; r++)
       for (int w = wL; w <= wU; w++) m = fmaxf(m, tile[(r * W + w) * C + c]);
     out[e] = m;
   }
@@ -261,14 +276,21 @@ int LaunchLrnMaxPool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, 
   QCNN_CHECK(N >= 1 && ksz >= 1 && stride >= 1 && size >= 1, "qcnn_lrn_maxpool: bad arguments");
   const int Ho = PoolOut(H, pad, ksz, stride), Wo = PoolOut(W, pad, ksz, stride);
   const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
-  const size_t tileBytes = sizeof(float) * static_cast<size_t>(ksz) * W * C;
+  // output rows per CTA: as many as keep two CTAs per SM (less re-normalisation of shared input rows)
+  int ro = 1;
+  static const int roMax = getenv("QCNN_LRN_RO") ? atoi(getenv("QCNN_LRN_RO")) : 1;
+  static const int lrnThreads = getenv("QCNN_LRN_THREADS") ? atoi(getenv("QCNN_LRN_THREADS")) : 512;   // measured: 512 > 384 > 256 threads
+  while (ro < roMax && ro < Ho && sizeof(float) * static_cast<size_t>(ro * stride + ksz) * W * C <= 110 * 1024) ro++;
+  const size_t tileBytes = sizeof(float) * static_cast<size_t>((ro - 1) * stride + ksz) * W * C;
   if (tileBytes <= 160 * 1024 && N <= 65535) {
     // specialised 8-channel path for the 5-wide window every reference table uses (CaffePara.cc:31,35,...)
-    auto kern = (size == 5 && C % 8 == 0) ? lrn_maxpool_tiled_kernel<5> : lrn_maxpool_tiled_kernel<0>;
+    const bool fast = beta == 0.75f;
+    auto kern = (size == 5 && C % 8 == 0) ? (fast ? lrn_maxpool_tiled_kernel<5, true> : lrn_maxpool_tiled_kernel<5, false>)
+                                          : lrn_maxpool_tiled_kernel<0, false>;
     if (tileBytes > 48 * 1024)
       QCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileBytes));
-    kern<<<dim3(Ho, N), kThreads, tileBytes, st>>>(src, dst, H, W, C, Ho, Wo, size, alpha / size, k, -beta, ksz, pad,
-                                                   stride);
+    kern<<<dim3(CeilDiv(Ho, ro), N), lrnThreads, tileBytes, st>>>(src, dst, H, W, C, Ho, Wo, size, alpha / size, k, -beta,
+                                                                ksz, pad, stride, ro);
   } else {
     lrn_maxpool_kernel<<<GridFor(ctx, total), kThreads, 0, st>>>(src, dst, N, H, W, C, Ho, Wo, size, alpha / size, k,
                                                                  -beta, ksz, pad, stride);

@@ -84,13 +84,15 @@ def test_alexnet_synthetic_weights_all_feature_maps(po, qcnn, ctx, synth_dir, mo
     p1 = net.forward(imgd[1:2].contiguous()).cpu().numpy()
     assert np.abs(p1[0] - prob_f[1]).max() <= PT
     # (d) host-buffer entry point (H2D + chunked pipeline + D2H) == device entry point
+    #     (chunks of 2 + 1 images run with their own tilings / kernel families, hence the mode's tolerance)
     net.set_chunk(2)
     ph = net.forward_host(img)
-    assert np.abs(ph - prob_f).max() <= 2e-6
+    HT = 5e-6 if mode == "strict" else PT
+    assert np.abs(ph - prob_f).max() <= HT
     pin = torch.from_numpy(img).pin_memory()
     out = torch.empty((N, 1000), dtype=torch.float32).pin_memory()
     net.forward_host(pin, out)
-    assert np.abs(out.numpy() - prob_f).max() <= 2e-6
+    assert np.abs(out.numpy() - prob_f).max() <= HT
     net.close()
 
 

@@ -11,7 +11,8 @@ batch-sharded, weights replicated, and for N > 1 the only exchange is one all-ga
 (NCCL over NVLink) inside the step.  One JSON line is printed by rank 0 (see the task contract):
   value     device-resident images/s, whole job (inputs already in HBM), CUDA events, max over ranks
   e2e       the same metric through the host-buffer C-ABI call qcnn_net_forward_h (pinned host in -> host out)
-  roofline  dominant kernel: algorithmic bytes / CUDA-event time vs the measured HBM peak (+ the smem-gather bound)
+  roofline  dominant kernel: executed tensor flops (decode-at-use GEMM) or algorithmic bytes / CUDA-event time vs the
+            measured peaks of MEASURED_PEAKS.json
   cpu_baseline  the reference's own CPU path timed on this box (rank 0, N = 1 only, bounded sample)
 `--impl reference` times the reference CPU implementation with all host cores instead (no GPU work at all).
 """
@@ -377,23 +378,56 @@ def run_b200_arm(args, q):
     pq_layers = [l for l in ALEXNET_PQ if layer_ms[l] > 0]
     dom = max(pq_layers, key=lambda l: layer_ms[l])
     wd = net.layer_work(dom, B)
-    achieved = wd["alg_bytes"] / (layer_ms[dom] * 1e-3) / 1e9
     sm_clk = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-    gather_peak = 32.0 * ctx.sm_count * sm_clk * 1e6       # conflict-free 4-byte shared-memory lookups per second
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(names[dom])
     except (OSError, ValueError, KeyError):
         pass
-    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
-                "alg_bytes_per_launch": wd["alg_bytes"], "ms_per_launch": round(float(layer_ms[dom]), 4),
-                "secondary_bound": {"resource": "shared-memory gather (32 lookups/clk/SM)",
-                                    "achieved_lookups_per_s": wd["lookups"] / (layer_ms[dom] * 1e-3),
-                                    "peak_lookups_per_s": gather_peak,
-                                    "frac": round(wd["lookups"] / (layer_ms[dom] * 1e-3) / gather_peak, 4)},
-                "note": "batched PQ layers are bound by on-chip LUT gather, not HBM (SURVEY.md 7.1); the HBM-bound "
-                        "kernel is the batch-1 FC assignment stream, reported in fc_b1"}
+
+    # Tensor-core work of a pq_gemm_tc launch, from the plan the library reports: every CTA runs `ksteps` k-steps of
+    # three kind::tf32 MMAs (3xTF32) of 128 channels x NT positions x 8: executed MACs, padding included.
+    import re
+
+    def tc_macs(l):
+        m = re.search(r"pq_gemm_tc.*?NT=(\d+).*?grid=(\d+).*?ksteps=(\d+)", net.pq_layer(l).describe(B))
+        return None if not m else float(m.group(2)) * float(m.group(3)) * 3.0 * 128.0 * float(m.group(1)) * 8.0
+    for l in pq_layers:
+        tm = tc_macs(l)
+        if tm:
+            per_layer[names[l]]["tensor_TFLOPs_executed"] = round(2.0 * tm / (layer_ms[l] * 1e-3) / 1e12, 1)
+    hbm = {"alg_bytes_per_launch": wd["alg_bytes"], "achieved_GBps": round(wd["alg_bytes"] / (layer_ms[dom] * 1e-3) / 1e9, 2),
+           "peak_GBps": hbm_peak, "frac": round(wd["alg_bytes"] / (layer_ms[dom] * 1e-3) / 1e9 / hbm_peak, 5),
+           "peak_source": peak_src}
+    dom_macs = tc_macs(dom)
+    if dom_macs:
+        # tf32 MMAs run at half the bf16 rate: peak = measured dense bf16 (cuBLAS, MEASURED_PEAKS.json) / 2
+        bf16 = float(peaks.get("bf16_tflops", 1650.0))
+        peak_tc = bf16 / 2.0
+        ach = 2.0 * dom_macs / (layer_ms[dom] * 1e-3) / 1e12
+        all_tc = [(tc_macs(l), layer_ms[l]) for l in pq_layers if tc_macs(l)]
+        roofline = {"bound": "tensor", "kernel": "pq_gemm_tc_kernel (%s)" % names[dom], "achieved": round(ach, 1),
+                    "peak": round(peak_tc, 1), "unit": "TFLOP/s", "frac": round(ach / peak_tc, 4), "traffic": traffic,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops / 2" if "bf16_tflops" in peaks else "fallback 1650 / 2") +
+                                   " (kind::tf32 issues at half the bf16 rate; nominal at %d MHz: %.0f)" %
+                                   (sm_clk, 2 * 2048 * ctx.sm_count * sm_clk * 1e6 / 1e12),
+                    "flops_per_launch": 2.0 * dom_macs, "ms_per_launch": round(float(layer_ms[dom]), 4),
+                    "all_pq_gemm_launches": {"launches": len(all_tc),
+                                             "achieved": round(sum(2.0 * m for m, _ in all_tc) / (sum(t for _, t in all_tc) * 1e-3) / 1e12, 1),
+                                             "ms": round(float(sum(t for _, t in all_tc)), 4)},
+                    "hbm": hbm,
+                    "note": "executed 3xTF32 tensor-core flops (padding included) of the decode-at-use GEMM; the same launch "
+                            "against the HBM roofline is in `hbm` (algorithmic bytes of SURVEY.md 8(d))"}
+    else:
+        gather_peak = 32.0 * ctx.sm_count * sm_clk * 1e6       # conflict-free 4-byte shared-memory lookups per second
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": hbm["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "alg_bytes_per_launch": wd["alg_bytes"], "ms_per_launch": round(float(layer_ms[dom]), 4),
+                    "secondary_bound": {"resource": "shared-memory gather (32 lookups/clk/SM)",
+                                        "achieved_lookups_per_s": wd["lookups"] / (layer_ms[dom] * 1e-3),
+                                        "peak_lookups_per_s": gather_peak,
+                                        "frac": round(wd["lookups"] / (layer_ms[dom] * 1e-3) / gather_peak, 4)},
+                    "note": "LUT + gather kernels are bound by on-chip LUT gather, not HBM (SURVEY.md 7.1)"}
 
     # ---- batch-1: latency and the HBM-bound FC assignment stream (L2 flushed between launches) ----
     extra = {}

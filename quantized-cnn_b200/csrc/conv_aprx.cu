@@ -1409,9 +1409,11 @@ int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
   if (int prc = PlanConv(L, N)) return prc;
   const ConvPlan& p = L->plan;
   if (p.kernel == 6) {
+    int ksteps = 0;
+    for (int c = 0; c < p.g.nChunks; c++) ksteps += p.g.chunkCount[p.g.mode == 1 ? c : 0];
     snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM) mode=%d NT=%d GT=%d slots=%d smem=%zuB grid=%d NPOS=%d "
-             "chunks=%d ksteps/chunk=%d", p.g.mode, p.g.NT, p.g.GT, p.g.NSLOT, p.smem,
-             CeilDiv(N * p.g.IB, p.g.NT) * L->grp * p.g.nct, p.g.NPOS, p.g.nChunks, p.g.chunkCount[0]);
+             "chunks=%d ksteps=%d", p.g.mode, p.g.NT, p.g.GT, p.g.NSLOT, p.smem,
+             CeilDiv(N * p.g.IB, p.g.NT) * L->grp * p.g.nct, p.g.NPOS, p.g.nChunks, ksteps);
     return 0;
   }
   if (p.kernel == 5) {

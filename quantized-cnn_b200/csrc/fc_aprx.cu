@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 
 namespace {
 
@@ -284,13 +285,31 @@ static int ChunkLen(int K, int tn) {
 // Large batches: the layer as a decode-at-use GEMM on the tensor cores (pq_gemm_tc.cu, mode 2): M = 128 outputs per CTA,
 // N = up to 256 images, K split over CTAs so that the grid fills the GPU; partial sums are reduced in fixed order by
 // fc_reduce_kernel.  QCNN_FC_TC=0 keeps the gather kernel, QCNN_FC_TC=1 forces the tensor-core path for any N.
+static bool FcTcEligible(const qcnn_layer* L, int N) {
+  static const char* env = getenv("QCNN_FC_TC");
+  if (env && env[0] == '0') return false;
+  if (!(env && env[0] == '1') && N < 96) return false;
+  if (L->opt_fc_nsplit || L->opt_fc_tn || L->opt_no_tc) return false;   // explicit gather-kernel tuning (fc_nsplit = 1: bit-exact reference order)
+  if (L->Din % 8 != 0 || !(L->d == 1 || L->d % 4 == 0) || L->S * L->d < L->Din || L->K > 256 || L->K % 4 != 0) return false;
+  return true;
+}
+
+// "pq_gemm_tc mode=2 ..." when batch N takes the tensor-core path, empty otherwise (bench / DESIGN bookkeeping)
+void DescribeFcTc(const qcnn_layer* L, int N, char* buf, size_t cap) {
+  buf[0] = 0;
+  if (!FcTcEligible(L, N)) return;
+  const int NT = std::min(256, RoundUp(N, 16)), KS = 4;
+  const int nct = CeilDiv(L->Dout, 128), tiles = CeilDiv(N, NT), kAll = L->Din / 8;
+  int nsplit = std::max(1, L->ctx->sm_count / (tiles * nct));
+  const int kPerSplit = RoundUp(CeilDiv(kAll, nsplit), KS);
+  nsplit = CeilDiv(kAll, kPerSplit);
+  snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM) mode=2 NT=%d GT=4 slots=4 grid=%d nsplit=%d ksteps=%d",
+           NT, tiles * nsplit * nct, nsplit, kPerSplit);
+}
+
 int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st, bool* handled) {
   *handled = false;
-  static const char* env = getenv("QCNN_FC_TC");
-  if (env && env[0] == '0') return 0;
-  if (!(env && env[0] == '1') && N < 96) return 0;
-  if (L->opt_fc_nsplit || L->opt_fc_tn || L->opt_no_tc) return 0;   // explicit gather-kernel tuning (fc_nsplit = 1: bit-exact reference order)
-  if (L->Din % 8 != 0 || !(L->d == 1 || L->d % 4 == 0) || L->S * L->d < L->Din || L->K > 256 || L->K % 4 != 0) return 0;
+  if (!FcTcEligible(L, N)) return 0;
   qcnn_ctx* ctx = L->ctx;
   const float* x = src;
   if (L->d_srcoff) {

@@ -140,6 +140,8 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   return m;
 }
 
+// DBG: cycle counters of the three roles (QCNN_GEMM_DBG=1) -- a separate instantiation, the production kernel reads no clocks
+template <bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const SmemMap sm = MapSmem(a);
@@ -402,18 +404,18 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
     fetchChunk(0);
     if (regPos) loadPos(0);
     if (nChunks > 1) fetchChunk(1);
-    long long sCp = 0, sEB = 0, sEC = 0, sT0 = clock64();
+    long long sCp = 0, sEB = 0, sEC = 0, sT0 = (DBG ? clock64() : 0ll);
     for (int kc = 0; kc < nChunks; kc++) {
       const int buf = kc & 1;
-      long long c0 = clock64();
+      long long c0 = (DBG ? clock64() : 0ll);
       if (kc + 1 < nChunks) asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk kc landed, kc+1 may be in flight
       else CpAsyncWaitAll();
       asm volatile("bar.sync 1, 96;" ::: "memory");     // every stager's copies of chunk kc have landed
-      sCp += clock64() - c0;
+      sCp += (DBG ? clock64() : 0ll) - c0;
       MbarArrive(fullC + kc % kCbBufs);                  // the decoders may start on chunk kc
-      c0 = clock64();
+      c0 = (DBG ? clock64() : 0ll);
       if (kc >= 2) MbarWait(emptyB + buf, ((kc >> 1) - 1) & 1);   // planes last read by the MMAs of chunk kc-2
-      sEB += clock64() - c0;
+      sEB += (DBG ? clock64() : 0ll) - c0;
       float4* pHi = planes + (buf * 2 + 0) * a.planeF4;
       float4* pLo = planes + (buf * 2 + 1) * a.planeF4;
       if (regPos && (a.dbgSkip & 2) && kc >= 2) {
@@ -444,14 +446,14 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       else asm volatile("bar.sync 1, 96;" ::: "memory");     // this raw buffer may be overwritten
       if (kc + 2 < nChunks) {
         const int nb = (kc + 2) % kCbBufs;
-        c0 = clock64();
+        c0 = (DBG ? clock64() : 0ll);
         if (kc + 2 >= kCbBufs) MbarWait(emptyC + nb, (((kc + 2) / kCbBufs) - 1) & 1);
-        sEC += clock64() - c0;
+        sEC += (DBG ? clock64() : 0ll) - c0;
         if ((a.dbgSkip & 2) && regPos) CpAsyncCommit(); else fetchChunk(kc + 2);
       }
     }
-    if (a.dbg && st == 0) {
-      atomicAdd(a.dbg + 8, static_cast<unsigned long long>(clock64() - sT0));
+    if (DBG && a.dbg && st == 0) {
+      atomicAdd(a.dbg + 8, static_cast<unsigned long long>((DBG ? clock64() : 0ll) - sT0));
       atomicAdd(a.dbg + 9, static_cast<unsigned long long>(sCp));
       atomicAdd(a.dbg + 10, static_cast<unsigned long long>(sEB));
       atomicAdd(a.dbg + 11, static_cast<unsigned long long>(sEC));
@@ -469,12 +471,12 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       const uint32_t planes0 = SmemU32(planes);
       int t = 0;
       uint32_t acc = 0;
-      long long wBC = 0, wA = 0, tStart = clock64();
+      long long wBC = 0, wA = 0, tStart = (DBG ? clock64() : 0ll);
       for (int kc = 0; kc < nChunks; kc++) {
         const int buf = kc & 1;
-        long long c0 = clock64();
+        long long c0 = (DBG ? clock64() : 0ll);
         MbarWait(fullB + buf, (kc >> 1) & 1);
-        wBC += clock64() - c0;
+        wBC += (DBG ? clock64() : 0ll) - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dHi = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 0) * a.planeF4) * 16u) >> 4) & 0x3FFFu);
         const uint64_t dLo = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 1) * a.planeF4) * 16u) >> 4) & 0x3FFFu);
@@ -482,9 +484,9 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kc : 0];
         for (int s0 = 0; s0 < ne; s0 += GT, t++) {
           const int slot = t % NSLOT;
-          c0 = clock64();
+          c0 = (DBG ? clock64() : 0ll);
           MbarWait(fullA + slot, (t / NSLOT) & 1);
-          wA += clock64() - c0;
+          wA += (DBG ? clock64() : 0ll) - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int n = min(GT, ne - s0);
           if (ElectOne()) {
@@ -509,14 +511,14 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
           __syncwarp();
         }
       }
-      if (a.dbg && lane == 0) {
-        const long long tIssue = clock64() - tStart;
-        long long c0 = clock64();
+      if (DBG && a.dbg && lane == 0) {
+        const long long tIssue = (DBG ? clock64() : 0ll) - tStart;
+        long long c0 = (DBG ? clock64() : 0ll);
         MbarWait(doneBar, 0);
         atomicAdd(a.dbg + 0, static_cast<unsigned long long>(tIssue));
         atomicAdd(a.dbg + 1, static_cast<unsigned long long>(wBC));
         atomicAdd(a.dbg + 2, static_cast<unsigned long long>(wA));
-        atomicAdd(a.dbg + 3, static_cast<unsigned long long>(clock64() - c0));
+        atomicAdd(a.dbg + 3, static_cast<unsigned long long>((DBG ? clock64() : 0ll) - c0));
         atomicAdd(a.dbg + 5, 1ull);
       }
     }
@@ -526,12 +528,12 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
     const int cc = min(c, CTv - 1);                 // rows beyond the valid channels decode a copy (never stored)
     const uint32_t laneBase = static_cast<uint32_t>(warp * 32) << 16;
     int t = 0;
-    long long dFC = 0, dEA = 0, dT0 = clock64();
+    long long dFC = 0, dEA = 0, dT0 = (DBG ? clock64() : 0ll);
     for (int kc = 0; kc < nChunks; kc++) {
       const int cbuf = kc % kCbBufs;
-      long long c0 = clock64();
+      long long c0 = (DBG ? clock64() : 0ll);
       MbarWait(fullC + cbuf, (kc / kCbBufs) & 1);
-      dFC += clock64() - c0;
+      dFC += (DBG ? clock64() : 0ll) - c0;
       const uint8_t* idb = ids + cbuf * a.idRows * 128 + cc;
       const float4* cb = cbs + cbuf * a.cbSlots * a.cbF4;
       const float* cbf = reinterpret_cast<const float*>(cb);
@@ -540,9 +542,9 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       for (int s0 = 0; s0 < ne; s0 += GT, t++) {
         const int slot = t % NSLOT;
         if (t >= NSLOT) {
-          c0 = clock64();
+          c0 = (DBG ? clock64() : 0ll);
           MbarWait(emptyA + slot, ((t / NSLOT) - 1) & 1);
-          dEA += clock64() - c0;
+          dEA += (DBG ? clock64() : 0ll) - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const int n = min(GT, ne - s0);
@@ -592,8 +594,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       }
       MbarArrive(emptyC + cbuf);
     }
-    if (a.dbg && tid == 0) {
-      atomicAdd(a.dbg + 12, static_cast<unsigned long long>(clock64() - dT0));
+    if (DBG && a.dbg && tid == 0) {
+      atomicAdd(a.dbg + 12, static_cast<unsigned long long>((DBG ? clock64() : 0ll) - dT0));
       atomicAdd(a.dbg + 13, static_cast<unsigned long long>(dFC));
       atomicAdd(a.dbg + 14, static_cast<unsigned long long>(dEA));
     }
@@ -761,7 +763,8 @@ int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N
   a.dstImg = static_cast<long long>(a.Ho) * a.Wo * a.Cout;
   const long long blocks = static_cast<long long>(CeilDiv(N * a.IB, a.NT)) * a.G * a.nct;
   QCNN_CHECK(blocks <= 2147483647LL, "qcnn_conv_aprx_forward: batch too large for the tensor-core tiling");
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   static const bool dbg = getenv("QCNN_GEMM_DBG") != nullptr;
   static const int skip = getenv("QCNN_GEMM_SKIP") ? atoi(getenv("QCNN_GEMM_SKIP")) : 0;
   a.dbgSkip = skip;
@@ -769,7 +772,8 @@ int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N
     QCNN_CUDA(cudaMalloc(&a.dbg, 128));
     QCNN_CUDA(cudaMemsetAsync(a.dbg, 0, 128, st));
   }
-  pq_gemm_tc_kernel<<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
+  if (dbg) pq_gemm_tc_kernel<true><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
+  else pq_gemm_tc_kernel<false><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
   QCNN_CUDA(cudaGetLastError());
   if (dbg) {
     unsigned long long h[16];
@@ -790,8 +794,8 @@ size_t PqGemmSmemBytes(const GemmArgs& a) { return static_cast<size_t>(MapSmem(a
 int LaunchPqGemmArgs(const GemmArgs& a, long long blocks, cudaStream_t st) {
   const size_t smem = PqGemmSmemBytes(a);
   QCNN_CHECK(blocks >= 1 && blocks <= 2147483647LL, "pq_gemm_tc: bad grid");
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pq_gemm_tc_kernel<<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(a);
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pq_gemm_tc_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(a);
   QCNN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -245,7 +245,9 @@ int qcnn_layer_set_param(qcnn_layer* L, const char* name, int value) {
 int qcnn_layer_describe(qcnn_layer* L, int N, char* buf, size_t cap) {
   QCNN_CHECK(L && buf && cap > 0 && N >= 1, "qcnn_layer_describe: bad argument");
   if (L->kind == QCNN_KIND_CONV) return DescribeConv(L, N, buf, cap);
-  snprintf(buf, cap, "fc_aprx Din=%d Dout=%d S=%d K=%d d=%d", L->Din, L->Dout, L->S, L->K, L->d);
+  char tc[256];
+  DescribeFcTc(L, N, tc, sizeof(tc));
+  snprintf(buf, cap, "fc_aprx Din=%d Dout=%d S=%d K=%d d=%d%s%s", L->Din, L->Dout, L->S, L->K, L->d, tc[0] ? " via " : "", tc);
   return 0;
 }
 

@@ -181,6 +181,7 @@ int LaunchConvDec(const ConvPlan& p, const ConvArgs& a, cudaStream_t st);
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
 size_t PqGemmSmemBytes(const GemmArgs& a);
 int LaunchPqGemmArgs(const GemmArgs& a, long long blocks, cudaStream_t st);
+void DescribeFcTc(const qcnn_layer* L, int N, char* buf, size_t cap);
 int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st, bool* handled);
 int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st);
 

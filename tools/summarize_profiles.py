@@ -54,7 +54,7 @@ def traffic_json(rep, out_path):
     out, i = {}, 0
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
-        if "reduce" in name or i >= len(order):
+        if "reduce" in name or "flatten" in name or i >= len(order):
             continue
 
         def mb(col):
@@ -84,7 +84,10 @@ def stage_split(rep, out_path, title):
         f.write("# " + title + "\n")
         for k in kern:
             h = k["hdr"]
-            i_s, i_e, i_w = h.index("# Samples"), h.index("Instructions Executed"), h.index("L1 Wavefronts Shared")
+            if not h or "# Samples" not in h or "Instructions Executed" not in h:
+                continue
+            i_s, i_e = h.index("# Samples"), h.index("Instructions Executed")
+            i_w = h.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in h else None
             tot = sum(int(r[i_s] or 0) for r in k["ins"])
             tote = sum(int(r[i_e] or 0) for r in k["ins"])
             if (k["name"], tot) in seen or tot == 0:
@@ -102,7 +105,7 @@ def stage_split(rep, out_path, title):
                 d = regs.setdefault(reg, {"s": 0, "e": 0, "w": 0, "ops": collections.Counter()})
                 d["s"] += int(r[i_s] or 0)
                 d["e"] += int(r[i_e] or 0)
-                d["w"] += int(r[i_w] or 0)
+                d["w"] += int(r[i_w] or 0) if i_w is not None else 0
                 d["ops"][op.split(".")[0]] += int(r[i_e] or 0)
                 if op.startswith("BAR"):
                     reg += 1

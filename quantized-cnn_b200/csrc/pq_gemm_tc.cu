@@ -20,7 +20,7 @@
 //              consecutive channels of one position: 128 B).
 // Shared-memory traffic per k-step is the B operand only (NT x 32 B per MMA = 64 B/clk at the MMA floor) plus the
 // decoders' index / codeword reads, so the tensor pipe, not shared memory, is the limit (the first version of this
-// kernel kept the decoded weights in shared memory and was bound by operand fetch: profiles/r01_dec_tc_v1.md).
+// kernel kept the decoded weights in shared memory and was bound by operand fetch: profiles/README.md, "dec_tc v1").
 //
 // Layer geometries are expressed as a table of k-steps (KStep: B start / half distance inside the staged planes, index
 // row and codebook slot of either half), so one main loop serves
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       CpAsyncCommit();
     };
     // Positions of the convolution modes: global -> registers -> hi/lo planes.  (16-byte cp.async of scattered pieces
-    // costs one shared-memory wavefront per THREAD -- profiles/r01_pq_gemm_staging.md -- whereas a 128-bit store of 32
+    // costs one shared-memory wavefront per THREAD -- profiles/README.md, "staging" -- whereas a 128-bit store of 32
     // consecutive float4 costs four per warp.)  A thread owns float4 st, st+96, ...: at most kRegPos of them.
     float4 rg[kRegPos];
     int poffR[kRegPos];        // chunk-invariant source offset of the thread's float4 (mode 0: incl. the half's +4)
@@ -462,8 +462,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
     // =========================== MMA issuer ===========================
     // The whole warp runs the loop on warp-uniform values (k-step table read from the kernel parameters, i.e. the
     // constant bank, so descriptors stay in uniform registers); one elected lane issues the tcgen05 instructions.
-    // (Issuing from a single divergent thread wraps every UTCHMMA in an elect loop plus R2UR moves: ~160 clk per MMA,
-    //  above the 128 clk the MMA itself takes -- profiles/r01_pq_gemm_issue.md.)
+    // (Issued from a single divergent thread, every UTCHMMA is wrapped in an ELECT / BRA.U.ANY loop with R2UR moves; in
+    //  this form the SASS issues them back to back -- profiles/README.md, "MMA issue".)
     {
       // instruction descriptor: D = F32, A = B = TF32, K-major, N = NT, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) | (8u << 24);

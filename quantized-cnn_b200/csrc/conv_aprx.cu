@@ -1412,8 +1412,9 @@ int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
     int ksteps = 0;
     for (int c = 0; c < p.g.nChunks; c++) ksteps += p.g.chunkCount[p.g.mode == 1 ? c : 0];
     snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM) mode=%d NT=%d GT=%d slots=%d smem=%zuB grid=%d NPOS=%d "
-             "chunks=%d ksteps=%d", p.g.mode, p.g.NT, p.g.GT, p.g.NSLOT, p.smem,
-             CeilDiv(N * p.g.IB, p.g.NT) * L->grp * p.g.nct, p.g.NPOS, p.g.nChunks, ksteps);
+             "chunks=%d ksteps=%d nsplit=%d", p.g.mode, p.g.NT, p.g.GT, p.g.NSLOT, p.smem,
+             CeilDiv(N * p.g.IB, p.g.NT) * L->grp * p.g.nct * std::max(1, p.g.nsplit), p.g.NPOS, p.g.nChunks,
+             ksteps / std::max(1, p.g.nsplit), std::max(1, p.g.nsplit));
     return 0;
   }
   if (p.kernel == 5) {

@@ -285,6 +285,17 @@ static int ChunkLen(int K, int tn) {
 // Large batches: the layer as a decode-at-use GEMM on the tensor cores (pq_gemm_tc.cu, mode 2): M = 128 outputs per CTA,
 // N = up to 256 images, K split over CTAs so that the grid fills the GPU; partial sums are reduced in fixed order by
 // fc_reduce_kernel.  QCNN_FC_TC=0 keeps the gather kernel, QCNN_FC_TC=1 forces the tensor-core path for any N.
+// dst[r][c] = sum over splits of partial[split][r][c] (+ ReLU); split 0 carries the bias.  Also used by the K-split
+// convolutions of pq_gemm_tc (rows = positions).
+int LaunchSplitReduce(qcnn_ctx* ctx, const float* partial, float* dst, int rows, int cols, int colsPad, int nsplit, int relu,
+                      cudaStream_t st) {
+  const int total = rows * cols;
+  fc_reduce_kernel<<<CeilDiv(total, 256), 256, 0, st>>>(partial, dst, rows, cols, colsPad, nsplit, relu);
+  QCNN_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
 static bool FcTcEligible(const qcnn_layer* L, int N) {
   static const char* env = getenv("QCNN_FC_TC");
   if (env && env[0] == '0') return false;

@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   int b = blockIdx.x;
   const int ct = b % a.nct; b /= a.nct;
   int g = 0, split = 0;
-  if (a.mode == 2) { split = b % a.nsplit; b /= a.nsplit; } else { g = b % a.G; b /= a.G; }
+  if (a.nsplit > 1) { split = b % a.nsplit; b /= a.nsplit; }
+  if (a.mode != 2) { g = b % a.G; b /= a.G; }
   const int tile = b;
   const int ch0 = ct * 128;                            // first channel of the tile inside the group
   const int CTv = min(128, a.Kg - ch0);                // valid channels
@@ -181,8 +182,13 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   // mode 2: this CTA's k-step range [k0, k0 + kTotal) of the layer; partial sums go to their own plane
   const int k0 = split * a.kPerSplit;
   const int kTotal = a.mode == 2 ? min(a.kPerSplit, a.kAll - k0) : 0;
-  const int nChunks = a.mode == 2 ? (kTotal + a.chunkCount[0] - 1) / a.chunkCount[0] : a.nChunks;
+  // convolution modes: K split by chunks [kcBase, kcBase + nChunks) (small batches: more CTAs than position tiles)
+  const int kcBase = a.mode == 2 ? 0 : split * a.kPerSplit;
+  const int nChunks = a.mode == 2 ? (kTotal + a.chunkCount[0] - 1) / a.chunkCount[0]
+                                  : (a.nsplit > 1 ? min(a.kPerSplit, a.nChunks - kcBase) : a.nChunks);
   if (a.mode == 2 && a.nsplit > 1) dstBase = a.partial + (static_cast<size_t>(split) * a.N + Q0) * a.dstRow + ch0;
+  if (a.mode != 2 && a.nsplit > 1)
+    dstBase = a.partial + (static_cast<size_t>(split) * a.N + i0) * a.dstImg + g * a.Kg + ch0;
 
   // ---- set-up (all threads) ----
   for (int e = tid; e < a.ntab; e += kThreads) tabS[e] = a.tab[e];
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       if (a.mode == 0) {
         // per-chunk scalars: the two 4-channel halves, their subspaces and the offsets inside the codewords
         const int taps = a.ksz * a.ksz;
-        const int chA = kc * 8, chB = kc * 8 + 4;
+        const int chA = (kcBase + kc) * 8, chB = chA + 4;
         const bool okA = chA < a.Cg, okB = chB < a.Cg;
         const int sA = okA ? chA / a.d : 0, jA = okA ? chA - sA * a.d : 0;
         const int sB = okB ? chB / a.d : 0, jB = okB ? chB - sB * a.d : 0;
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       }
       if (a.mode == 1) {
         // chunk = phase row ph: pixels of input rows r*stride + ph - pad, one 4-byte copy per channel
-        const int ph = kc;
+        const int ph = kcBase + kc;
         // (positions travel through registers: loadPos / storePos)
         // codebook: slot 0 = the first 4 floats of every codeword of subspace 0, slot 1 = zeros (unpaired taps)
         float4* cdst = cbs + cbuf * a.cbSlots * K;
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
     }
     auto loadPos = [&](int kc) {
       if (a.mode == 0) {
-        const int chA = kc * 8;
+        const int chA = (kcBase + kc) * 8;
         uint32_t m = pvalid;
         if (chA >= a.Cg) m = 0;
         else if (chA + 4 >= a.Cg) m &= ~phalf;
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
           if ((m >> i) & 1u) rg[i] = __ldg(reinterpret_cast<const float4*>(srcG + poffR[i]));
         }
       } else {
-        const int ph = kc;
+        const int ph = kcBase + kc;
         const float* srcG = srcBase + static_cast<size_t>(g) * a.Cg * a.chStride + ph * a.rowStride;
 #pragma unroll
         for (int i = 0; i < kRegPos; i++) {
@@ -480,8 +486,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dHi = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 0) * a.planeF4) * 16u) >> 4) & 0x3FFFu);
         const uint64_t dLo = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 1) * a.planeF4) * 16u) >> 4) & 0x3FFFu);
-        const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0];
-        const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kc : 0];
+        const int e0 = a.chunkFirst[a.mode == 1 ? kcBase + kc : 0];
+        const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kcBase + kc : 0];
         for (int s0 = 0; s0 < ne; s0 += GT, t++) {
           const int slot = t % NSLOT;
           c0 = (DBG ? clock64() : 0ll);
@@ -537,8 +543,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       const uint8_t* idb = ids + cbuf * a.idRows * 128 + cc;
       const float4* cb = cbs + cbuf * a.cbSlots * a.cbF4;
       const float* cbf = reinterpret_cast<const float*>(cb);
-      const int e0 = a.chunkFirst[a.mode == 1 ? kc : 0];
-      const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kc : 0];
+      const int e0 = a.chunkFirst[a.mode == 1 ? kcBase + kc : 0];
+      const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kcBase + kc : 0];
       for (int s0 = 0; s0 < ne; s0 += GT, t++) {
         const int slot = t % NSLOT;
         if (t >= NSLOT) {
@@ -695,10 +701,19 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
         ga.ntab = ne;
         p.smem = static_cast<size_t>(MapSmem(ga).total);
         if (p.smem > smemMax0) continue;
-        p.a.CT = 128; p.a.nct = ga.nct; p.a.R = NT; p.a.nstrips = GT; p.a.rgroups = 1;
-        const double perCta = ne * 3.0 * (NT / 2.0) * 1.15 + 120.0 * ne / GT + 9000.0 + NT * 24.0;
-        const double ctas = static_cast<double>(CeilDiv(N * IB, NT)) * G * ga.nct;
-        cands->emplace_back(perCta * std::ceil(ctas / L->ctx->sm_count), p);
+        p.a.CT = 128; p.a.nct = ga.nct; p.a.R = NT; p.a.nstrips = GT;
+        const double ctas0 = static_cast<double>(CeilDiv(N * IB, NT)) * G * ga.nct;
+        // small batches: split the phase rows over CTAs (partial sums reduced by LaunchSplitReduce)
+        for (int nsplit = 1; nsplit <= st; nsplit *= 2) {
+          if (nsplit > 1 && ctas0 * nsplit > 1.5 * L->ctx->sm_count) break;
+          ga.kPerSplit = CeilDiv(st, nsplit);
+          ga.nsplit = CeilDiv(st, ga.kPerSplit);
+          if (ga.nsplit != nsplit) continue;
+          p.a.rgroups = nsplit;
+          const double perCta = ne * 3.0 * (NT / 2.0) * 1.15 / nsplit + 120.0 * ne / GT / nsplit + 9000.0 + NT * 24.0 +
+                                (nsplit > 1 ? 6000.0 : 0.0);
+          cands->emplace_back(perCta * std::ceil(ctas0 * nsplit / L->ctx->sm_count), p);
+        }
       }
     }
     return;
@@ -740,20 +755,29 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
       ga.nct = CeilDiv(Kg, 128);
       p.smem = static_cast<size_t>(MapSmem(ga).total);
       if (p.smem > smemMax) continue;
-      p.a.CT = 128; p.a.nct = ga.nct; p.a.R = NT; p.a.nstrips = GT; p.a.rgroups = 1;   // (candidate de-duplication keys)
+      p.a.CT = 128; p.a.nct = ga.nct; p.a.R = NT; p.a.nstrips = GT;   // (candidate de-duplication keys)
       const double ksteps = static_cast<double>(ga.nChunks) * taps;
-      const double perCta = ksteps * 3.0 * (NT / 2.0) * 1.1 + 120.0 * ksteps / GT + 4000.0 + NT * 24.0;
-      const double ctas = static_cast<double>(CeilDiv(N * IB, NT)) * G * ga.nct;
-      const double waves = std::ceil(ctas / L->ctx->sm_count);
-      cands->emplace_back(perCta * waves, p);
+      const double ctas0 = static_cast<double>(CeilDiv(N * IB, NT)) * G * ga.nct;
+      // small batches: split the 8-channel chunks over CTAs (partial sums reduced by LaunchSplitReduce)
+      for (int nsplit = 1; nsplit <= ga.nChunks; nsplit *= 2) {
+        if (nsplit > 1 && ctas0 * nsplit > 1.5 * L->ctx->sm_count) break;
+        ga.kPerSplit = CeilDiv(ga.nChunks, nsplit);
+        ga.nsplit = CeilDiv(ga.nChunks, ga.kPerSplit);
+        if (ga.nsplit != nsplit) continue;
+        p.a.rgroups = nsplit;
+        const double perCta = ksteps * 3.0 * (NT / 2.0) * 1.1 / nsplit + 120.0 * ksteps / GT / nsplit + 4000.0 + NT * 24.0 +
+                              (nsplit > 1 ? 6000.0 : 0.0);
+        cands->emplace_back(perCta * std::ceil(ctas0 * nsplit / L->ctx->sm_count), p);
+      }
     }
   }
 }
 
-int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st) {
+int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st) {
   GemmArgs a = p.g;
   a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
-  a.N = N; a.relu = relu;
+  a.N = N; a.relu = a.nsplit > 1 ? 0 : relu;
+  if (a.nsplit < 1) a.nsplit = 1;
   a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
   a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = L->grp; a.Cg = L->Cin / L->grp; a.Kg = L->Cout / L->grp;
   a.KgPad = RoundUp(a.Kg, 16); a.S = L->S; a.K = L->K; a.d = L->d;
@@ -761,8 +785,18 @@ int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N
   if (L->src_nchw) { a.rowStride = a.Wi; a.colStride = 1; a.chStride = a.Hi * a.Wi; }
   else { a.rowStride = a.Wi * a.Cin; a.colStride = a.Cin; a.chStride = 1; }
   a.dstImg = static_cast<long long>(a.Ho) * a.Wo * a.Cout;
-  const long long blocks = static_cast<long long>(CeilDiv(N * a.IB, a.NT)) * a.G * a.nct;
+  const long long blocks = static_cast<long long>(CeilDiv(N * a.IB, a.NT)) * a.G * a.nct * a.nsplit;
   QCNN_CHECK(blocks <= 2147483647LL, "qcnn_conv_aprx_forward: batch too large for the tensor-core tiling");
+  if (a.nsplit > 1) {
+    const size_t need = sizeof(float) * static_cast<size_t>(a.nsplit) * N * a.dstImg;
+    if (need > L->partial_bytes) {
+      if (L->d_partial) QCNN_CUDA(cudaFree(L->d_partial));
+      L->d_partial = nullptr; L->partial_bytes = 0;
+      QCNN_CUDA(cudaMalloc(&L->d_partial, need));
+      L->partial_bytes = need;
+    }
+    a.partial = L->d_partial;
+  }
   QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   static const bool dbg = getenv("QCNN_GEMM_DBG") != nullptr;
@@ -786,6 +820,8 @@ int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N
             h[10] / n, h[11] / n, h[12] / n, h[13] / n, h[14] / n);
     cudaFree(a.dbg);
   }
+  if (a.nsplit > 1)
+    return LaunchSplitReduce(L->ctx, a.partial, dst, N * a.Ho * a.Wo, a.Cout, a.Cout, a.nsplit, relu, st);
   return 0;
 }
 

@@ -181,9 +181,11 @@ int LaunchConvDec(const ConvPlan& p, const ConvArgs& a, cudaStream_t st);
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
 size_t PqGemmSmemBytes(const GemmArgs& a);
 int LaunchPqGemmArgs(const GemmArgs& a, long long blocks, cudaStream_t st);
+int LaunchSplitReduce(qcnn_ctx* ctx, const float* partial, float* dst, int rows, int cols, int colsPad, int nsplit, int relu,
+                      cudaStream_t st);
 void DescribeFcTc(const qcnn_layer* L, int N, char* buf, size_t cap);
 int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st, bool* handled);
-int LaunchPqGemm(const qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st);
+int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st);
 
 int LaunchRelu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, cudaStream_t st);
 int LaunchLrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha, float beta,

@@ -238,13 +238,35 @@ __global__ void fc_reduce_kernel(const float* __restrict__ partial, float* __res
   dst[i] = relu ? fmaxf(v, 0.0f) : v;
 }
 
-// dst[n][f] = src[n*Din + srcoff[f]]: NHWC-mapped source -> the flat [N][Din] rows the tensor-core path stages
-__global__ void fc_flatten_kernel(const float* __restrict__ src, const int* __restrict__ srcoff, float* __restrict__ dst,
-                                  int N, int Din) {
+// Activations of the tensor-core FC path, pre-split (3xTF32 hi / lo) and laid out as the shared-memory plane image of
+// every (image tile, k-chunk): [tile][chunk][hi, lo][2*KS halves][NT images] float4, so that a CTA stages a chunk with
+// ONE bulk copy.  Folds the NHWC -> NCHW-flatten map of the first FC layer (srcoff) and zero-pads images / features.
+__global__ void fc_prep_kernel(const float* __restrict__ src, const int* __restrict__ srcoff, float4* __restrict__ dst,
+                               int N, int Din, int NT, int KS, int nChunksAll, int tiles) {
+  const size_t per = static_cast<size_t>(2 * KS) * NT;                       // float4 per plane (hi or lo)
+  const size_t total = static_cast<size_t>(tiles) * nChunksAll * per;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<size_t>(N) * Din) return;
-  const int n = static_cast<int>(i / Din), f = static_cast<int>(i - static_cast<size_t>(n) * Din);
-  dst[i] = __ldg(src + static_cast<size_t>(n) * Din + __ldg(srcoff + f));
+  if (i >= total) return;
+  const size_t blk = i / per;
+  const int r = static_cast<int>(i - blk * per);
+  const int ih = r / NT, n = r - ih * NT;
+  const int tile = static_cast<int>(blk / nChunksAll), chunk = static_cast<int>(blk - static_cast<size_t>(tile) * nChunksAll);
+  const int Q = tile * NT + n, f = (chunk * KS * 2 + ih) * 4;
+  float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (Q < N) {
+    const float* row = src + static_cast<size_t>(Q) * Din;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (f + j < Din) v[j] = __ldg(row + (srcoff ? __ldg(srcoff + f + j) : f + j));
+  }
+  float4 hi, lo;
+  hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); lo.x = v[0] - hi.x;
+  hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); lo.y = v[1] - hi.y;
+  hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); lo.z = v[2] - hi.z;
+  hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); lo.w = v[3] - hi.w;
+  float4* base = dst + blk * per * 2;
+  base[r] = hi;
+  base[per + r] = lo;
 }
 
 template <int K, int CPT, int TN, int PF, bool PRE>
@@ -309,12 +331,12 @@ static bool FcTcEligible(const qcnn_layer* L, int N) {
 void DescribeFcTc(const qcnn_layer* L, int N, char* buf, size_t cap) {
   buf[0] = 0;
   if (!FcTcEligible(L, N)) return;
-  const int NT = std::min(256, RoundUp(N, 16)), KS = 4;
+  const int NT = std::min(256, RoundUp(N, 16)), KS = 3;
   const int nct = CeilDiv(L->Dout, 128), tiles = CeilDiv(N, NT), kAll = L->Din / 8;
   int nsplit = std::max(1, L->ctx->sm_count / (tiles * nct));
   const int kPerSplit = RoundUp(CeilDiv(kAll, nsplit), KS);
   nsplit = CeilDiv(kAll, kPerSplit);
-  snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM) mode=2 NT=%d GT=4 slots=4 grid=%d nsplit=%d ksteps=%d",
+  snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM) mode=2 NT=%d GT=3 slots=5 grid=%d nsplit=%d ksteps=%d",
            NT, tiles * nsplit * nct, nsplit, kPerSplit);
 }
 
@@ -322,32 +344,35 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   *handled = false;
   if (!FcTcEligible(L, N)) return 0;
   qcnn_ctx* ctx = L->ctx;
-  const float* x = src;
-  if (L->d_srcoff) {
-    const size_t need = sizeof(float) * static_cast<size_t>(N) * L->Din;
+  const int KS = 3;                 // k-steps per chunk (plane image of a chunk: 2 * 3 halves x NT images, hi + lo)
+  const int NTq = std::min(256, RoundUp(N, 16));
+  const int tilesq = CeilDiv(N, NTq), nChunksAll = CeilDiv(L->Din / 8, KS);
+  {
+    const size_t per = static_cast<size_t>(2 * KS) * NTq;
+    const size_t total = static_cast<size_t>(tilesq) * nChunksAll * per;
+    const size_t need = total * 2 * sizeof(float4);
     if (need > L->flat_bytes) {
       if (L->d_flat) QCNN_CUDA(cudaFree(L->d_flat));
       L->d_flat = nullptr; L->flat_bytes = 0;
       QCNN_CUDA(cudaMalloc(&L->d_flat, need));
       L->flat_bytes = need;
     }
-    const size_t total = static_cast<size_t>(N) * L->Din;
-    fc_flatten_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, L->d_srcoff, L->d_flat, N, L->Din);
+    fc_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, L->d_srcoff, reinterpret_cast<float4*>(L->d_flat),
+                                                                            N, L->Din, NTq, KS, nChunksAll, tilesq);
     QCNN_CUDA(cudaGetLastError());
     ctx->launches++;
-    x = L->d_flat;
   }
   GemmArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = 2;
-  a.src = x; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
+  a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
   a.N = N; a.Cin = L->Din; a.Cout = L->Dout; a.G = 1; a.Cg = L->Din; a.Kg = L->Dout; a.KgPad = L->DoutPad;
   a.S = L->S; a.K = L->K; a.d = L->d; a.kshift = L->kshift;
   a.srcImg = L->Din; a.dstImg = 0;
   a.IB = 1; a.PW = 1;
-  a.NT = std::min(256, RoundUp(N, 16));
-  const int KS = 4;
-  a.GT = 4; a.NSLOT = 4;
+  a.NT = NTq;
+  a.GT = 3; a.NSLOT = 5;
+  a.nPB = 3; a.xprep = L->d_flat; a.nChunksAll = nChunksAll;
   a.planeF4 = KS * 2 * a.NT;
   a.NPOS = a.NT;
   a.cbSlots = L->d == 1 ? 8 * KS : 2 * KS;

@@ -13,7 +13,7 @@
 //              TMEM (16 columns per k-step: 8 hi + 8 lo).  Decoded weights never touch shared memory.
 //   warp 4     one thread issues tcgen05.mma (kind::tf32, M = 128 channels, N = NT positions, K = 8) with A in TMEM and
 //              B = the position planes in shared memory; three MMAs per k-step (3xTF32: Ah*Bh + Ah*Bl + Al*Bh).
-//   warps 5-7  stagers: cp.async the next chunk's positions (raw) + codebook slices + index rows, split the positions
+//   warps 5-7  stagers: load the next chunk's positions (global -> registers), cp.async its codebook slices + index rows, split the positions
 //              into hi/lo planes (K-major, SWIZZLE_NONE core matrices: 8 positions x 16 B, SBO = 128 B, LBO = distance
 //              between the two halves), double-buffered against the MMAs of the current chunk.
 //   all warps  epilogue: TMEM (lane = channel, column = position) -> + bias, ReLU -> NHWC stores (a warp writes 32
@@ -125,8 +125,8 @@ struct SmemMap {  // byte offsets inside the dynamic shared memory
 __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   SmemMap m;
   int o = 0;
-  m.planes = o; o += 2 * 2 * a.planeF4 * 16;            // [buf][hi,lo][planeF4]
-  m.raw = o;    o += a.mode == 2 ? 2 * a.planeF4 * 16 : 0;   // mode 2: [2] cp.async targets of the positions (two chunks in flight)
+  m.planes = o; o += a.nPB * 2 * a.planeF4 * 16;        // [buf][hi,lo][planeF4]
+  m.raw = o;
   m.cbs = o;    o += kCbBufs * a.cbSlots * a.cbF4 * 16; // [cbuf][slot][cbF4] codeword pieces (raw fp32)
   m.ids = o;    o += kCbBufs * a.idRows * 128;          // [cbuf][row][128 channels] assignment indices
   m.tab = o;    o += a.ntab * 16;
@@ -134,7 +134,7 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   m.posrow = o; o += a.mode == 1 ? a.planeF4 * 4 : 0;   // mode 1: first input row of the position (phase row 0)
   m.outoff = o; o += 256 * 4;                           // destination element offset of every position (-1: none)
   m.bias = o;   o += 128 * 4;
-  m.bars = o;   o += 8 * (2 * kMaxSlots + 2 * kCbBufs + 5);
+  m.bars = o;   o += 8 * (2 * kMaxSlots + 2 * kCbBufs + 7);
   m.tmem = o;   o += 16;
   m.total = o;
   return m;
@@ -149,8 +149,6 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   const int K = a.K, NT = a.NT, GT = a.GT, NSLOT = a.NSLOT;
 
   float4* planes = reinterpret_cast<float4*>(smem + sm.planes);
-  float4* rawAll = reinterpret_cast<float4*>(smem + sm.raw);
-  float4* raw = rawAll;
   float4* cbs = reinterpret_cast<float4*>(smem + sm.cbs);
   uint8_t* ids = smem + sm.ids;
   KStep* tabS = reinterpret_cast<KStep*>(smem + sm.tab);
@@ -161,8 +159,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + sm.bars);   // [kMaxSlots] decoders -> issuer
   uint64_t* emptyA = fullA + kMaxSlots;                            // [kMaxSlots] MMAs retired -> decoders
   uint64_t* fullB = emptyA + kMaxSlots;                            // [2] position planes: stagers -> issuer
-  uint64_t* emptyB = fullB + 2;                                    // [2] chunk's MMAs retired -> stagers
-  uint64_t* fullC = emptyB + 2;                                    // [kCbBufs] codebook + indices: stagers -> decoders
+  uint64_t* emptyB = fullB + 3;                                    // [<=3] chunk's MMAs retired -> stagers
+  uint64_t* fullC = emptyB + 3;                                    // [kCbBufs] codebook + indices: stagers -> decoders
   uint64_t* emptyC = fullC + kCbBufs;                              // [kCbBufs] decoders done with the chunk -> stagers
   uint64_t* doneBar = emptyC + kCbBufs;
   uint32_t* tmemBase = reinterpret_cast<uint32_t*>(smem + sm.tmem);
@@ -237,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   }
   if (tid == 0) {
     for (int i = 0; i < kMaxSlots; i++) { MbarInit(fullA + i, kDecoders); MbarInit(emptyA + i, 1); }
-    for (int i = 0; i < 2; i++) { MbarInit(fullB + i, kStagers); MbarInit(emptyB + i, 1); }
+    for (int i = 0; i < 3; i++) { MbarInit(fullB + i, kStagers); MbarInit(emptyB + i, 1); }
     for (int i = 0; i < kCbBufs; i++) { MbarInit(fullC + i, kStagers); MbarInit(emptyC + i, kDecoders); }
     MbarInit(doneBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -252,11 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   if (warpU >= 5) {
     // =========================== stagers ===========================
     const int st = tid - kStager0;
-    // chunk kc: positions (raw) + codebook slices + index rows, all by cp.async (one group)
+    // chunk kc: codebook slices + index rows by cp.async (one group); the positions travel through registers
     auto fetchChunk = [&](int kc) {
       const int cbuf = kc % kCbBufs;
-      float4* raw = rawAll + (kc & 1) * a.planeF4;
-      (void)raw;
       if (a.mode == 0) {
         // per-chunk scalars: the two 4-channel halves, their subspaces and the offsets inside the codewords
         const int taps = a.ksz * a.ksz;
@@ -313,13 +309,6 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         const int KS = a.chunkCount[0];
         const int ne = min(KS, kTotal - kc * KS);
         const int f0 = (k0 + kc * KS) * 8;
-        const float* srcG = srcBase + f0;
-        const int lim = ne * 2 * NT;          // float4 beyond the chunk's k-steps are not read by any MMA
-#pragma unroll 2
-        for (int p = st; p < lim; p += kStagers) {
-          const int off = posoff[p];
-          CpAsync16(raw + p, srcG + (off >= 0 ? off : 0), off >= 0);
-        }
         const int gran = (CTv + 15) >> 4;
         if (a.d == 1) {
           // slot q = subspace f0 + q: its K scalar codewords; index row q
@@ -359,14 +348,18 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
     int prowR[kRegPos];        // mode 1: first input row (phase row 0), very negative when the column is outside
     uint32_t pvalid = 0;       // mode 0: bit i = the float4 exists and its position is inside an image
     uint32_t phalf = 0;        // mode 0: bit i = second half (channels 4..7 of the chunk)
-    if (a.mode != 2) {
+    {
 #pragma unroll
       for (int i = 0; i < kRegPos; i++) {
         const int p = st + i * kStagers;
         poffR[i] = 0; prowR[i] = -(1 << 28);
         if (p < a.planeF4) {
           const int off = posoff[p];
-          if (a.mode == 0) {
+          if (a.mode == 2) {
+            poffR[i] = off;
+            prowR[i] = p / NT;                     // (k-step, half) index inside the chunk
+            if (off >= 0) pvalid |= 1u << i;
+          } else if (a.mode == 0) {
             const bool hb = p >= a.NPOS;
             poffR[i] = off + (hb ? 4 : 0);
             if (off >= 0) pvalid |= 1u << i;
@@ -379,7 +372,16 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       }
     }
     auto loadPos = [&](int kc) {
-      if (a.mode == 0) {
+      if (a.mode == 2) {
+        const int KS = a.chunkCount[0];
+        const int ne = min(KS, kTotal - kc * KS);
+        const float* srcG = srcBase + (k0 + kc * KS) * 8;
+#pragma unroll
+        for (int i = 0; i < kRegPos; i++) {
+          rg[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (((pvalid >> i) & 1u) && prowR[i] < 2 * ne) rg[i] = __ldg(reinterpret_cast<const float4*>(srcG + poffR[i]));
+        }
+      } else if (a.mode == 0) {
         const int chA = (kcBase + kc) * 8;
         uint32_t m = pvalid;
         if (chA >= a.Cg) m = 0;
@@ -406,25 +408,37 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         }
       }
     };
-    const bool regPos = a.mode != 2;
+    const bool regPos = true;
     fetchChunk(0);
-    if (regPos) loadPos(0);
+    if (a.mode != 2) loadPos(0);
     if (nChunks > 1) fetchChunk(1);
     long long sCp = 0, sEB = 0, sEC = 0, sT0 = (DBG ? clock64() : 0ll);
     for (int kc = 0; kc < nChunks; kc++) {
-      const int buf = kc & 1;
+      const int buf = kc % a.nPB;
       long long c0 = (DBG ? clock64() : 0ll);
       if (kc + 1 < nChunks) asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk kc landed, kc+1 may be in flight
       else CpAsyncWaitAll();
-      asm volatile("bar.sync 1, 96;" ::: "memory");     // every stager's copies of chunk kc have landed
+      // (each stager arrives after its own copies have landed; the barrier completes when all 96 have)
       sCp += (DBG ? clock64() : 0ll) - c0;
       MbarArrive(fullC + kc % kCbBufs);                  // the decoders may start on chunk kc
       c0 = (DBG ? clock64() : 0ll);
-      if (kc >= 2) MbarWait(emptyB + buf, ((kc >> 1) - 1) & 1);   // planes last read by the MMAs of chunk kc-2
+      if (kc >= a.nPB) MbarWait(emptyB + buf, ((kc / a.nPB) - 1) & 1);   // planes last read by the MMAs of chunk kc-nPB
       sEB += (DBG ? clock64() : 0ll) - c0;
       float4* pHi = planes + (buf * 2 + 0) * a.planeF4;
       float4* pLo = planes + (buf * 2 + 1) * a.planeF4;
-      if (regPos && (a.dbgSkip & 2) && kc >= 2) {
+      if (a.mode == 2) {
+        // the plane image of (tile, chunk) was written by fc_prep_kernel: one bulk copy (hi + lo, contiguous) straight
+        // into the planes, completion counted on the same mbarrier the stagers arrive on
+        if (st == 0) {
+          const uint32_t bytes = static_cast<uint32_t>(a.planeF4) * 32u;
+          const float* gsrc = a.xprep + (static_cast<size_t>(tile) * a.nChunksAll + (k0 / a.chunkCount[0] + kc)) * a.planeF4 * 8;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemU32(fullB + buf)), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(SmemU32(pHi)), "l"(gsrc), "r"(bytes), "r"(SmemU32(fullB + buf)) : "memory");
+        } else {
+          MbarArrive(fullB + buf);
+        }
+      } else if (regPos && (a.dbgSkip & 2) && kc >= 2) {
       } else if (regPos) {
 #pragma unroll
         for (int i = 0; i < kRegPos; i++) {
@@ -436,20 +450,12 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
             pLo[p] = lo;
           }
         }
-      } else {
-        const float4* rawK = rawAll + buf * a.planeF4;
-#pragma unroll 2
-        for (int p = st; p < a.planeF4; p += kStagers) {
-          float4 hi, lo;
-          SplitTf32x4(rawK[p], hi, lo);
-          pHi[p] = hi;
-          pLo[p] = lo;
-        }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // planes are read by the tensor core
-      MbarArrive(fullB + buf);
-      if (regPos) { if (kc + 1 < nChunks && !((a.dbgSkip & 2) && kc >= 1)) loadPos(kc + 1); }
-      else asm volatile("bar.sync 1, 96;" ::: "memory");     // this raw buffer may be overwritten
+      if (a.mode != 2) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // planes are read by the tensor core
+        MbarArrive(fullB + buf);
+        if (kc + 1 < nChunks && !((a.dbgSkip & 2) && kc >= 1)) loadPos(kc + 1);
+      }
       if (kc + 2 < nChunks) {
         const int nb = (kc + 2) % kCbBufs;
         c0 = (DBG ? clock64() : 0ll);
@@ -479,9 +485,9 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       uint32_t acc = 0;
       long long wBC = 0, wA = 0, tStart = (DBG ? clock64() : 0ll);
       for (int kc = 0; kc < nChunks; kc++) {
-        const int buf = kc & 1;
+        const int buf = kc % a.nPB;
         long long c0 = (DBG ? clock64() : 0ll);
-        MbarWait(fullB + buf, (kc >> 1) & 1);
+        MbarWait(fullB + buf, (kc / a.nPB) & 1);
         wBC += (DBG ? clock64() : 0ll) - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dHi = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 0) * a.planeF4) * 16u) >> 4) & 0x3FFFu);
@@ -678,7 +684,7 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
         if (ga.planeF4 > kRegPos * kStagers) continue;
         ga.cbSlots = 2; ga.idRows = rowsPer * L->ksz;
         ga.nChunks = st;
-        ga.K = L->K; ga.cbF4 = L->K;
+        ga.K = L->K; ga.cbF4 = L->K; ga.nPB = 2;
         ga.nct = CeilDiv(Kg, 128);
         int ne = 0;
         for (int ph = 0; ph < st; ph++) {
@@ -751,7 +757,7 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
         ks.idx0 = static_cast<short>(t); ks.idx1 = static_cast<short>(taps + t);
         ks.cb0 = 0; ks.cb1 = 1;
       }
-      ga.K = L->K; ga.cbF4 = L->K;
+      ga.K = L->K; ga.cbF4 = L->K; ga.nPB = 2;
       ga.nct = CeilDiv(Kg, 128);
       p.smem = static_cast<size_t>(MapSmem(ga).total);
       if (p.smem > smemMax) continue;

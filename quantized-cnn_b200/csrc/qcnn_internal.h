@@ -111,6 +111,9 @@ struct GemmArgs {
   int kshift;                   // stored assignment byte = index << kshift
   float* partial;               // mode 2, nsplit > 1: [nsplit][N][dstRow]
   int dstRow;                   // mode 2: floats per destination row
+  int nPB;                      // position-plane buffers (2; 3 for mode 2, whose planes arrive by bulk copy)
+  const float* xprep;           // mode 2: activations pre-split into the plane image (fc_prep_kernel), [tile][chunk][hi,lo][2KS][NT][4]
+  int nChunksAll;               // mode 2: chunks of the whole layer (xprep indexing)
   int cbF4;                     // float4 per codebook slot (K for d % 4 == 0 pieces, K/4 for d == 1 scalars)
   int NT;                     // positions per CTA = MMA N (multiple of 16, <= 256)
   int NPOS;                   // staged positions per plane (NT + halo)
@@ -160,7 +163,7 @@ struct qcnn_layer {
   // FC scratch
   float* d_partial;
   size_t partial_bytes;
-  float* d_flat;         // tensor-core FC path: source gathered into [N][Din] (NHWC-mapped sources only)
+  float* d_flat;         // tensor-core FC path: source pre-split into hi/lo plane images (fc_prep_kernel)
   size_t flat_bytes;
   // tuning overrides (0 = automatic)
   int opt_fc_nsplit;

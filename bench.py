@@ -185,8 +185,10 @@ def _ref_worker(args):
 def cpu_reference_single_thread(dirpath, pfx, images, warmup=2):
     """The reference's CalcFeatMap path, ONE pinned thread, batch 1 (it has no batching: kDataCntInBatch = 1)."""
     from oracle import pyoracle as po
+    saved = None
     try:
-        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[-1]})
+        saved = os.sched_getaffinity(0)
+        os.sched_setaffinity(0, {sorted(saved)[-1]})
     except (AttributeError, OSError):
         pass
     kind = "reference" if po.have_ref() else "port"
@@ -207,7 +209,8 @@ def cpu_reference_single_thread(dirpath, pfx, images, warmup=2):
                 ms.append((time.perf_counter() - t0) * 1e3)
         ms = np.asarray(ms)
     try:
-        os.sched_setaffinity(0, set(range(os.cpu_count())))
+        if saved:
+            os.sched_setaffinity(0, saved)
     except (AttributeError, OSError):
         pass
     return kind, float(np.median(ms)), float(ms.min())
@@ -284,6 +287,18 @@ def run_b200_arm(args, q):
     dirpath, pfx, what = model_files(q, tmp)
     ctx = q.Context(local)
     net = q.Net(ctx, dirpath, pfx, "AlexNet")
+
+    # NUMA placement of the pinned staging buffers: run this rank on the CPUs next to its GPU (NVML's ideal affinity)
+    # before anything is pinned -- on a two-socket host a remote pinned buffer copies at ~30 instead of ~55 GB/s
+    # (tools/h2d_bw.py), and the end-to-end number is bound by that copy
+    numa = "unbound"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa = "bound to %d GPU-local cpus" % len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001  (no NVML / not permitted: keep the default placement)
+        pass
 
     # two alternating input sets per rank (distinct images per rank), generated on the host, pinned
     tables = lcg_tables(IMG_LEN)
@@ -483,7 +498,7 @@ def run_b200_arm(args, q):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, what, world),
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * IMG_LEN * 4,
-                    "d2h_bytes_per_step": B * 1000 * 4},
+                    "d2h_bytes_per_step": B * 1000 * 4, "host_buffers": "pinned, " + numa},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "per_layer": per_layer,
             "extra": extra, "impl": "b200",

@@ -460,6 +460,21 @@ def run_b200_arm(args, q):
             b.record()
             torch.cuda.synchronize()
             lat.append(a.elapsed_time(b))
+        extra["latency_b1_eager_ms"] = round(float(np.median(lat)), 4)
+        # same call on a non-default stream: after two eager passes the library replays a captured CUDA graph
+        side = torch.cuda.Stream(device=dev)
+        lat = []
+        with torch.cuda.stream(side):
+            for w in range(5):
+                net.forward(one, prob=p1)
+            side.synchronize()
+            for k in range(30):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(side)
+                net.forward(one, prob=p1)
+                b.record(side)
+                side.synchronize()
+                lat.append(a.elapsed_time(b))
         extra["latency_b1_ms"] = round(float(np.median(lat)), 4)
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
         net.set_profiling(True)

@@ -355,6 +355,7 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
       if (L->d_flat) QCNN_CUDA(cudaFree(L->d_flat));
       L->d_flat = nullptr; L->flat_bytes = 0;
       QCNN_CUDA(cudaMalloc(&L->d_flat, need));
+      L->ctx->alloc_epoch++;
       L->flat_bytes = need;
     }
     fc_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, L->d_srcoff, reinterpret_cast<float4*>(L->d_flat),
@@ -403,6 +404,7 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
       if (L->d_partial) QCNN_CUDA(cudaFree(L->d_partial));
       L->d_partial = nullptr; L->partial_bytes = 0;
       QCNN_CUDA(cudaMalloc(&L->d_partial, need));
+      L->ctx->alloc_epoch++;
       L->partial_bytes = need;
     }
     a.partial = L->d_partial;
@@ -462,6 +464,7 @@ int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaS
       L->d_partial = nullptr;
       L->partial_bytes = 0;
       QCNN_CUDA(cudaMalloc(&L->d_partial, need));
+      L->ctx->alloc_epoch++;
       L->partial_bytes = need;
     }
     a.partial = L->d_partial;

@@ -13,9 +13,10 @@
 //              TMEM (16 columns per k-step: 8 hi + 8 lo).  Decoded weights never touch shared memory.
 //   warp 4     one thread issues tcgen05.mma (kind::tf32, M = 128 channels, N = NT positions, K = 8) with A in TMEM and
 //              B = the position planes in shared memory; three MMAs per k-step (3xTF32: Ah*Bh + Ah*Bl + Al*Bh).
-//   warps 5-7  stagers: load the next chunk's positions (global -> registers), cp.async its codebook slices + index rows, split the positions
-//              into hi/lo planes (K-major, SWIZZLE_NONE core matrices: 8 positions x 16 B, SBO = 128 B, LBO = distance
-//              between the two halves), double-buffered against the MMAs of the current chunk.
+//   warps 5-7  stagers: the next chunk's positions go global -> registers -> hi/lo planes (K-major, SWIZZLE_NONE core
+//              matrices: 8 positions x 16 B, SBO = 128 B, LBO = distance between the two halves), double-buffered against
+//              the MMAs of the current chunk; codebook slices + index rows by cp.async, four chunks deep.  FC layers: the
+//              planes were pre-split by fc_prep_kernel and arrive by one cp.async.bulk per chunk (three buffers).
 //   all warps  epilogue: TMEM (lane = channel, column = position) -> + bias, ReLU -> NHWC stores (a warp writes 32
 //              consecutive channels of one position: 128 B).
 // Shared-memory traffic per k-step is the B operand only (NT x 32 B per MMA = 64 B/clk at the MMA floor) plus the
@@ -43,7 +44,6 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kDecoders = 128;   // warps 0-3
-constexpr int kIssuer = 128;     // first lane of warp 4
 constexpr int kStagers = 96;     // warps 5-7
 constexpr int kStager0 = 160;
 constexpr int kMaxSlots = 5;
@@ -55,10 +55,6 @@ __device__ __forceinline__ uint32_t SmemU32(const void* p) { return static_cast<
 __device__ __forceinline__ void CpAsync16(void* smemDst, const void* gsrc, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0: nothing is read, the 16 destination bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(SmemU32(smemDst)), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void CpAsync4(void* smemDst, const void* gsrc, bool valid) {
-  const int sz = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(SmemU32(smemDst)), "l"(gsrc), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void CpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -120,13 +116,12 @@ __device__ __forceinline__ void StoreWeights(uint32_t taddr, const float4 w0, co
 }
 
 struct SmemMap {  // byte offsets inside the dynamic shared memory
-  int planes, raw, cbs, ids, tab, posoff, posrow, outoff, bias, bars, tmem, total;
+  int planes, cbs, ids, tab, posoff, posrow, outoff, bias, bars, tmem, total;
 };
 __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   SmemMap m;
   int o = 0;
   m.planes = o; o += a.nPB * 2 * a.planeF4 * 16;        // [buf][hi,lo][planeF4]
-  m.raw = o;
   m.cbs = o;    o += kCbBufs * a.cbSlots * a.cbF4 * 16; // [cbuf][slot][cbF4] codeword pieces (raw fp32)
   m.ids = o;    o += kCbBufs * a.idRows * 128;          // [cbuf][row][128 channels] assignment indices
   m.tab = o;    o += a.ntab * 16;
@@ -210,12 +205,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       const bool colOk = i < a.N && wi >= 0 && wi < a.Wi;
       off = static_cast<int>((i - i0) * a.srcImg) + (r * a.stride - a.pad) * a.rowStride + wi * a.colStride;
       posrow[p] = colOk ? r * a.stride - a.pad : -(1 << 28);
-    } else {
-      // float4 p = ((k-step i, half), image n): features [8i + 4 half, +4) of the chunk, image Q0 + n
-      const int n = p % NT, ih = p / NT;
-      if (Q0 + n < a.N) off = n * a.Cin + ih * 4;
     }
-    posoff[p] = off;
+    posoff[p] = off;   // (mode 2 stages its planes by bulk copy: no offsets)
   }
   for (int p = tid; p < 256; p += kThreads) {
     int off = -1;
@@ -348,18 +339,14 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
     int prowR[kRegPos];        // mode 1: first input row (phase row 0), very negative when the column is outside
     uint32_t pvalid = 0;       // mode 0: bit i = the float4 exists and its position is inside an image
     uint32_t phalf = 0;        // mode 0: bit i = second half (channels 4..7 of the chunk)
-    {
+    if (a.mode != 2) {
 #pragma unroll
       for (int i = 0; i < kRegPos; i++) {
         const int p = st + i * kStagers;
         poffR[i] = 0; prowR[i] = -(1 << 28);
         if (p < a.planeF4) {
           const int off = posoff[p];
-          if (a.mode == 2) {
-            poffR[i] = off;
-            prowR[i] = p / NT;                     // (k-step, half) index inside the chunk
-            if (off >= 0) pvalid |= 1u << i;
-          } else if (a.mode == 0) {
+          if (a.mode == 0) {
             const bool hb = p >= a.NPOS;
             poffR[i] = off + (hb ? 4 : 0);
             if (off >= 0) pvalid |= 1u << i;
@@ -372,16 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       }
     }
     auto loadPos = [&](int kc) {
-      if (a.mode == 2) {
-        const int KS = a.chunkCount[0];
-        const int ne = min(KS, kTotal - kc * KS);
-        const float* srcG = srcBase + (k0 + kc * KS) * 8;
-#pragma unroll
-        for (int i = 0; i < kRegPos; i++) {
-          rg[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-          if (((pvalid >> i) & 1u) && prowR[i] < 2 * ne) rg[i] = __ldg(reinterpret_cast<const float4*>(srcG + poffR[i]));
-        }
-      } else if (a.mode == 0) {
+      if (a.mode == 0) {
         const int chA = (kcBase + kc) * 8;
         uint32_t m = pvalid;
         if (chA >= a.Cg) m = 0;
@@ -408,7 +386,6 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         }
       }
     };
-    const bool regPos = true;
     fetchChunk(0);
     if (a.mode != 2) loadPos(0);
     if (nChunks > 1) fetchChunk(1);
@@ -438,8 +415,8 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         } else {
           MbarArrive(fullB + buf);
         }
-      } else if (regPos && (a.dbgSkip & 2) && kc >= 2) {
-      } else if (regPos) {
+      } else if ((a.dbgSkip & 2) && kc >= 2) {
+      } else {
 #pragma unroll
         for (int i = 0; i < kRegPos; i++) {
           const int p = st + i * kStagers;
@@ -461,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         c0 = (DBG ? clock64() : 0ll);
         if (kc + 2 >= kCbBufs) MbarWait(emptyC + nb, (((kc + 2) / kCbBufs) - 1) & 1);
         sEC += (DBG ? clock64() : 0ll) - c0;
-        if ((a.dbgSkip & 2) && regPos) CpAsyncCommit(); else fetchChunk(kc + 2);
+        if ((a.dbgSkip & 2) && a.mode != 2) CpAsyncCommit(); else fetchChunk(kc + 2);
       }
     }
     if (DBG && a.dbg && st == 0) {
@@ -799,6 +776,7 @@ int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, floa
       if (L->d_partial) QCNN_CUDA(cudaFree(L->d_partial));
       L->d_partial = nullptr; L->partial_bytes = 0;
       QCNN_CUDA(cudaMalloc(&L->d_partial, need));
+      L->ctx->alloc_epoch++;
       L->partial_bytes = need;
     }
     a.partial = L->d_partial;

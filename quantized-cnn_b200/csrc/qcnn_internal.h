@@ -42,6 +42,7 @@ struct qcnn_ctx {
   int cc_major, cc_minor;
   size_t smem_optin;  // max dynamic shared memory per block (opt-in)
   unsigned long long launches;  // kernels launched through this ctx (monotonic)
+  unsigned long long alloc_epoch;  // bumped whenever a device scratch buffer is (re)allocated: captured graphs go stale
 };
 
 enum { QCNN_KIND_CONV = 0, QCNN_KIND_FC = 1 };

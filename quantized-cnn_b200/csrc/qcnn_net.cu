@@ -15,6 +15,8 @@
 #include "../host/CaffePara.h"
 #include "qcnn_internal.h"
 
+#include <cstdlib>
+
 using namespace qcnn;
 
 struct NetLayer {
@@ -45,6 +47,16 @@ struct qcnn_net {
   cudaStream_t stCopy, stComp;
   cudaEvent_t evH2D[2], evDone[2];
   int chunk;
+  // small batches: the launch sequence of a forward pass is captured once per (N, buffers, stream) and replayed
+  struct GraphEntry {
+    int N; const float* img; float* prob; float* logits; cudaStream_t st;
+    unsigned long long epoch; // ctx->alloc_epoch at capture
+    int seen;                 // eager passes so far (tilings are autotuned and scratch is allocated during these)
+    int disabled;             // capture failed once: stay eager
+    cudaGraphExec_t exec;
+    unsigned long long launches;
+  };
+  std::vector<GraphEntry> graphs;
 };
 
 static size_t MapElems(const NetLayer& L) { return static_cast<size_t>(L.Hout) * L.Wout * L.Cout; }
@@ -60,6 +72,7 @@ static void FreeMaps(qcnn_net* net) {
 static int EnsureCapacity(qcnn_net* net, int N) {
   if (N <= net->capN) return 0;
   FreeMaps(net);
+  net->ctx->alloc_epoch++;
   const size_t L = net->layers.size();
   net->maps.assign(L + 1, nullptr);
   QCNN_CUDA(cudaMalloc(&net->maps[0], sizeof(float) * N * net->imgC * net->imgH * net->imgW));
@@ -211,6 +224,7 @@ void qcnn_net_destroy(qcnn_net* net) {
     if (net->d_in[i]) cudaFree(net->d_in[i]);
     if (net->stCopy) { cudaEventDestroy(net->evH2D[i]); cudaEventDestroy(net->evDone[i]); }
   }
+  for (qcnn_net::GraphEntry& g : net->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (net->d_prob) cudaFree(net->d_prob);
   if (net->d_logit) cudaFree(net->d_logit);
   if (net->stCopy) cudaStreamDestroy(net->stCopy);
@@ -245,11 +259,79 @@ qcnn_layer* qcnn_net_pq_layer(qcnn_net* net, int l) {
 
 int qcnn_net_launch_count(const qcnn_net* net) { return net ? static_cast<int>(net->lastLaunches) : 0; }
 
+static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, float* logits, cudaStream_t st);
+
+// Batches of <= kGraphMaxN images are launch-bound (20 kernels of 10-30 us): after two eager passes (autotuning, scratch
+// allocation) the sequence is captured into a CUDA graph keyed by (N, buffers, stream) and replayed.  Not used on the
+// legacy default stream (it cannot be captured), while profiling / keeping maps, or with QCNN_GRAPH=0.
+constexpr int kGraphMaxN = 8;
+
 int qcnn_net_forward(qcnn_net* net, const float* img, int N, float* prob, float* logits, void* stream) {
   QCNN_CHECK(net && img && prob, "qcnn_net_forward: NULL argument");
   QCNN_CHECK(N >= 1, "qcnn_net_forward: N must be >= 1");
-  qcnn_ctx* ctx = net->ctx;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool graphsOn = !(getenv("QCNN_GRAPH") && getenv("QCNN_GRAPH")[0] == '0');
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st) cudaStreamIsCapturing(st, &cap);
+  if (!graphsOn || N > kGraphMaxN || st == nullptr || net->keep || net->profiling || cap != cudaStreamCaptureStatusNone)
+    return ForwardEager(net, img, N, prob, logits, st);
+  qcnn_net::GraphEntry* ge = nullptr;
+  for (qcnn_net::GraphEntry& g : net->graphs)
+    if (g.N == N && g.img == img && g.prob == prob && g.logits == logits && g.st == st) ge = &g;
+  if (!ge) {
+    if (net->graphs.size() >= 8) {   // bounded cache: drop the oldest entry
+      if (net->graphs.front().exec) cudaGraphExecDestroy(net->graphs.front().exec);
+      net->graphs.erase(net->graphs.begin());
+    }
+    net->graphs.push_back({N, img, prob, logits, st, 0, 0, 0, nullptr, 0});
+    ge = &net->graphs.back();
+  }
+  if (ge->exec && ge->epoch != net->ctx->alloc_epoch) {   // a scratch buffer moved since the capture
+    cudaGraphExecDestroy(ge->exec);
+    ge->exec = nullptr;
+    ge->seen = 1;
+  }
+  if (ge->exec) {
+    QCNN_CUDA(cudaGraphLaunch(ge->exec, st));
+    net->ctx->launches += ge->launches;
+    net->lastLaunches = ge->launches;
+    return 0;
+  }
+  if (ge->disabled || ge->seen < 2) {
+    ge->seen++;
+    return ForwardEager(net, img, N, prob, logits, st);
+  }
+  // third pass with the same arguments: capture, instantiate, replay
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    ge->disabled = 1;
+    return ForwardEager(net, img, N, prob, logits, st);
+  }
+  const int rc = ForwardEager(net, img, N, prob, logits, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    ge->disabled = 1;
+    return rc ? rc : ForwardEager(net, img, N, prob, logits, st);
+  }
+  ge->launches = net->lastLaunches;
+  ge->epoch = net->ctx->alloc_epoch;
+  const cudaError_t ie = cudaGraphInstantiate(&ge->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    ge->exec = nullptr;
+    ge->disabled = 1;
+    return ForwardEager(net, img, N, prob, logits, st);
+  }
+  QCNN_CUDA(cudaGraphLaunch(ge->exec, st));
+  return 0;
+}
+
+static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, float* logits, cudaStream_t st) {
+  qcnn_ctx* ctx = net->ctx;
   if (int rc = EnsureCapacity(net, N)) return rc;
   const int L = static_cast<int>(net->layers.size());
   const unsigned long long launches0 = ctx->launches;

@@ -83,6 +83,17 @@ def test_alexnet_synthetic_weights_all_feature_maps(po, qcnn, ctx, synth_dir, mo
     #     summation order -- are chosen per batch size, so "same" means within the parity tolerance)
     p1 = net.forward(imgd[1:2].contiguous()).cpu().numpy()
     assert np.abs(p1[0] - prob_f[1]).max() <= PT
+    # (c2) small batches on a non-default stream are replayed from a captured CUDA graph after two eager passes
+    side = torch.cuda.Stream()
+    one = imgd[1:2].contiguous()
+    pg = torch.empty((1, 1000), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for _ in range(5):
+            net.forward(one, prob=pg)
+            side.synchronize()
+            assert np.abs(pg.cpu().numpy()[0] - p1[0]).max() <= 1e-7
+        assert net.launch_count() > 0
     # (d) host-buffer entry point (H2D + chunked pipeline + D2H) == device entry point
     #     (chunks of 2 + 1 images run with their own tilings / kernel families, hence the mode's tolerance)
     net.set_chunk(2)

@@ -137,7 +137,7 @@ template <int SIZE, bool FAST075>
 __global__ void lrn_maxpool_tiled_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int C,
                                          int Ho, int Wo, int size, float coeff, float kini, float nbeta, int ksz,
                                          int pad, int stride, int ro) {
-  extern __shared__ float tile[];  // [rows][W][C]
+  extern __shared__ __align__(16) float tile[];  // [rows][W][C]
   const int ho0 = blockIdx.x * ro, n = blockIdx.y;
   const int hoN = min(Ho, ho0 + ro);
   const int hL = max(0, ho0 * stride - pad), hU = min(H, (hoN - 1) * stride + ksz - pad) - 1;
@@ -164,6 +164,27 @@ __global__ void lrn_maxpool_tiled_kernel(const float* __restrict__ src, float* _
   __syncthreads();
   const int rowOut = Wo * C;
   float* out = dst + (static_cast<size_t>(n) * Ho + ho0) * rowOut;
+  if ((C & 3) == 0) {
+    // four channels per thread: 128-bit shared-memory reads and global stores
+    const int c4n = C >> 2, rowOut4 = Wo * c4n;
+    const float4* tile4 = reinterpret_cast<const float4*>(tile);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    for (int e = threadIdx.x; e < (hoN - ho0) * rowOut4; e += blockDim.x) {
+      const int r0 = e / rowOut4, rem = e - r0 * rowOut4;
+      const int wo = rem / c4n, c4 = rem - wo * c4n;
+      const int ho = ho0 + r0;
+      const int rL = max(0, ho * stride - pad) - hL, rU = min(H, ho * stride + ksz - pad) - 1 - hL;
+      const int wL = max(0, wo * stride - pad), wU = min(W, wo * stride + ksz - pad) - 1;
+      float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      for (int r = rL; r <= rU; r++)
+        for (int w = wL; w <= wU; w++) {
+          const float4 v = tile4[(r * W + w) * c4n + c4];
+          m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+      out4[e] = m;
+    }
+    return;
+  }
   for (int e = threadIdx.x; e < (hoN - ho0) * rowOut; e += blockDim.x) {
     const int r0 = e / rowOut, rem = e - r0 * rowOut;
     const int wo = rem / C, c = rem - wo * C;

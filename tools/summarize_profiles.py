@@ -54,7 +54,7 @@ def traffic_json(rep, out_path):
     out, i = {}, 0
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
-        if "reduce" in name or "flatten" in name or i >= len(order):
+        if "reduce" in name or "flatten" in name or "fc_prep" in name or i >= len(order):
             continue
 
         def mb(col):

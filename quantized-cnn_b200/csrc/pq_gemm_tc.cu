@@ -460,6 +460,11 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       const uint32_t planes0 = SmemU32(planes);
       int t = 0;
       uint32_t acc = 0;
+      // NT <= 128 leaves room for a second accumulator: the hi*hi products go to D, the two cross terms to D + NT, and
+      // the epilogue adds them -- the tensor core's accumulation error grows with the number of chained MMAs per
+      // accumulator, and the chain of the dominant term is three times shorter this way
+      const uint32_t corrOff = NT <= 128 ? static_cast<uint32_t>(NT) : 0u;
+      uint32_t accCorr = 0;
       long long wBC = 0, wA = 0, tStart = (DBG ? clock64() : 0ll);
       for (int kc = 0; kc < nChunks; kc++) {
         const int buf = kc % a.nPB;
@@ -485,9 +490,10 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
                                    (static_cast<uint64_t>(static_cast<uint32_t>(ks.lbo)) << 16);
               const uint32_t aHi = tmemA + static_cast<uint32_t>((slot * GT + i) * 16), aLo = aHi + 8;
               UmmaTf32Ts(tmemD, aHi, dHi + off, idesc, acc);
-              UmmaTf32Ts(tmemD, aHi, dLo + off, idesc, 1u);
-              UmmaTf32Ts(tmemD, aLo, dHi + off, idesc, 1u);
+              UmmaTf32Ts(tmemD + corrOff, aHi, dLo + off, idesc, corrOff ? accCorr : 1u);
+              UmmaTf32Ts(tmemD + corrOff, aLo, dHi + off, idesc, 1u);
               acc = 1u;
+              accCorr = 1u;
             }
             // commits are issued by the thread that issued the MMAs they track
             UmmaCommit(emptyA + slot);
@@ -497,6 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
             }
           }
           acc = 1u;
+          accCorr = 1u;
           __syncwarp();
         }
       }
@@ -608,6 +615,17 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                    : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (NT <= 128) {   // second accumulator (cross terms of the 3xTF32 split)
+        uint32_t r2[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
+                       "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15])
+                     : "r"(taddr + static_cast<uint32_t>(NT)) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      }
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         const int off = outoff[blk * 16 + j];

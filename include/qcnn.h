@@ -102,6 +102,16 @@ QCNN_API int qcnn_fc_aprx_forward(qcnn_layer* layer, const float* src, int N, fl
 QCNN_API int qcnn_fc_aprx_forward_flat(qcnn_layer* layer, const float* src, int N, float* dst, int fuse_relu,
                                        void* stream);
 
+/* A run of consecutive FC layers of ONE forward pass (the FCnt [ReLU] [Drpt] iterations of the layer loop in
+ * CaffeEva::ExecForwardPass, src/CaffeEva.cc:213-261, each iteration being CalcFeatMap_FCntAprx :968-1025) as a single
+ * persistent launch; batch <= 4 (the latency path, bound by the HBM stream of the assignment matrices).  relu[l] != 0
+ * applies CalcFeatMap_ReLu after layer l.  src [N][Din of layers[0]] (or the NHWC map its set_src_nhwc folds),
+ * dst [N][Dout of layers[n-1]].  stamps (nullable, device, 2 * sm_count u64): %globaltimer at the first / last
+ * instruction of every CTA, for latency measurements.  Fails if the shapes are not supported by the fused kernel
+ * (qcnn_fc_aprx_forward per layer always works). */
+QCNN_API int qcnn_fc_chain_forward(qcnn_layer* const* layers, const int* relu, int n, const float* src, int N,
+                                   float* dst, unsigned long long* stamps, void* stream);
+
 /* ---- supporting layers (src/CaffeEva.cc:1027-1116, 870-921) ---------------------------------------------- */
 QCNN_API int qcnn_relu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, void* stream);
 QCNN_API int qcnn_lrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha,

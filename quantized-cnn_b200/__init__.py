@@ -76,6 +76,7 @@ _SIGS = {
     "qcnn_conv_aprx_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "qcnn_fc_aprx_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "qcnn_fc_aprx_forward_flat": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "qcnn_fc_chain_forward": (_i, [C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _vp, _vp, _vp]),
     "qcnn_relu": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "qcnn_lrn": (_i, [_vp, _vp, _vp, _sz, _i, _i, _f, _f, _f, _vp]),
     "qcnn_maxpool": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -293,6 +294,19 @@ class FcLayer(_Layer):
         y = torch.empty((N, self.Dout), dtype=torch.float32, device=x.device)
         _check(lib.qcnn_fc_aprx_forward(self.h, _dptr(x), N, _dptr(y), int(relu), _stream(stream)))
         return y
+
+
+def fc_chain_forward(layers, relu, x, stamps=None, stream=None):
+    """Consecutive FC layers (FcLayer objects) as one persistent launch; x [N<=4, Din]; returns [N, Dout of the last]."""
+    import torch
+    n = len(layers)
+    hs = (_vp * n)(*[l.h for l in layers])
+    rl = (_i * n)(*[int(r) for r in relu])
+    N = x.shape[0]
+    y = torch.empty((N, layers[-1].out_dims()[2]), dtype=torch.float32, device=x.device)
+    sp = C.c_void_p(stamps.data_ptr()) if stamps is not None else None
+    _check(lib.qcnn_fc_chain_forward(hs, rl, n, _dptr(x), N, _dptr(y), sp, _stream(stream)))
+    return y
 
 
 class Net(object):

@@ -1275,14 +1275,14 @@ int PlanConv(qcnn_layer* L, int N) {
       }
     }
   }
-  // decode-at-use implicit GEMM on the tensor cores (conv_dec_tc.cu)
-  {
-    const size_t before = cands.size();
-    if (!L->opt_no_tc) {
-      PlanConvDec(L, N, &cands);
-      PlanPqGemm(L, N, &cands);
-    }
-    found = found || cands.size() > before;
+  // decode-at-use GEMMs on the tensor cores (pq_gemm_tc.cu).  The kernel FAMILY is a setting, not a timing result:
+  // with tensor_core = 1 (default) an eligible layer always runs pq_gemm_tc (3xTF32; tolerance in DESIGN.md 2), with
+  // tensor_core = 0 always the LUT + gather kernels; on-device timing only chooses among tilings of that family, so the
+  // numerical path of a (layer, batch size) is the same in every process.
+  if (!L->opt_no_tc) {
+    std::vector<std::pair<double, ConvPlan>> tc;
+    PlanPqGemm(L, N, &tc);
+    if (!tc.empty()) { cands.swap(tc); found = true; }
   }
   QCNN_CHECK(found, "qcnn_conv_layer_create: no tiling fits (Cout/grp=%d must be a multiple of 16; K=%d must be a "
              "multiple of 8; k=%d, W=%d)", Kg, L->K, L->ksz, L->Win);
@@ -1291,11 +1291,14 @@ int PlanConv(qcnn_layer* L, int N) {
   std::stable_sort(cands.begin(), cands.end(), [](const std::pair<double, ConvPlan>& x, const std::pair<double, ConvPlan>& y) { return x.first < y.first; });
   if (!L->cands) L->cands = new std::vector<ConvPlan>();
   L->cands->clear();
-  // QCNN_FORCE_KERNEL=<0 s1 | 1 roll | 2 s1_tc | 3 roll_tc | 4 direct | 5 dec_tc | 6 pq_gemm_tc> restricts the choice (tests / experiments)
+  // layer parameter "force_kernel" / QCNN_FORCE_KERNEL=<0 s1 | 1 roll | 2 s1_tc | 3 roll_tc | 4 direct | 6 pq_gemm_tc>
+  // restricts the choice (tests pin the kernel they check; fails when that kernel has no tiling for the layer)
   const char* force = getenv("QCNN_FORCE_KERNEL");
-  if (force) {
+  if (L->opt_force_kernel || force) {
+    const int want = L->opt_force_kernel ? L->opt_force_kernel - 1 : atoi(force);
     std::vector<std::pair<double, ConvPlan>> kept;
-    for (const auto& c : cands) if (c.second.kernel == atoi(force)) kept.push_back(c);
+    for (const auto& c : cands) if (c.second.kernel == want) kept.push_back(c);
+    QCNN_CHECK(!kept.empty() || !L->opt_force_kernel, "qcnn_conv_aprx_forward: force_kernel=%d has no tiling for this layer at batch %d", want, N);
     if (!kept.empty()) cands.swap(kept);
   }
   // every kernel family that has a feasible tiling gets at least two seats among the candidates
@@ -1303,7 +1306,7 @@ int PlanConv(qcnn_layer* L, int N) {
     int perKernel[7] = {0, 0, 0, 0, 0, 0, 0};
     for (size_t i = 0; i < cands.size() && L->cands->size() < kMaxCand; i++) {
       ConvPlan c = cands[i].second;
-      if (pass == 0 && perKernel[c.kernel] >= (c.kernel == 4 ? 8 : (c.kernel == 5 ? 4 : (c.kernel == 6 ? 6 : 2)))) continue;
+      if (pass == 0 && perKernel[c.kernel] >= (c.kernel == 4 ? 8 : (c.kernel == 6 ? 6 : 2))) continue;
       ConvArgs& a = c.a;
       a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
       a.ksz = L->ksz; a.pad = L->pad; a.stride = L->stride; a.G = G; a.Cg = Cg; a.Kg = Kg;
@@ -1349,7 +1352,6 @@ static int LaunchPlan(qcnn_layer* L, const ConvPlan& p, const float* src, int N,
   a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
   a.N = N; a.relu = relu; a.src_nchw = L->src_nchw;
   if (p.kernel == 6) return LaunchPqGemm(L, p, src, N, dst, relu, st);
-  if (p.kernel == 5) return LaunchConvDec(p, a, st);
   if (p.kernel == 4) {
     const int nj = std::min(a.Cg, a.d);
     // p.J carries the output rows per thread (2 or 4)
@@ -1374,10 +1376,10 @@ int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   static const bool autotune = !(getenv("QCNN_AUTOTUNE") && getenv("QCNN_AUTOTUNE")[0] == '0');
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cap);
-  if (autotune && !L->tuned && L->cands && L->cands->size() > 1 && cap == cudaStreamCaptureStatusNone) {
+  if (autotune && !L->opt_no_autotune && !L->tuned && L->cands && L->cands->size() > 1 && cap == cudaStreamCaptureStatusNone) {
     cudaEvent_t e0, e1;
     QCNN_CUDA(cudaEventCreate(&e0));
-    QCNN_CUDA(cudaEventCreate(&e1));
+    if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return CudaFail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__); }
     float bestMs = 1e30f;
     size_t bestI = 0;
     for (size_t i = 0; i < L->cands->size(); i++) {
@@ -1389,9 +1391,9 @@ int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
       float ms = 1e30f;
       bool ok = true;
       for (int sample = 0; sample < 2 && ok; sample++) {
-        QCNN_CUDA(cudaEventRecord(e0, st));
+        if (cudaEventRecord(e0, st) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
         for (int r = 0; r < reps; r++) LaunchPlan(L, c, src, N, dst, relu, st);
-        QCNN_CUDA(cudaEventRecord(e1, st));
+        if (cudaEventRecord(e1, st) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
         float t = 0.0f;
         cudaEventElapsedTime(&t, e0, e1);
@@ -1423,12 +1425,6 @@ int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
              "chunks=%d ksteps=%d nsplit=%d", p.g.mode, p.g.NT, p.g.GT, p.g.NSLOT, p.smem,
              CeilDiv(N * p.g.IB, p.g.NT) * L->grp * p.g.nct * std::max(1, p.g.nsplit), p.g.NPOS, p.g.nChunks,
              ksteps / std::max(1, p.g.nsplit), std::max(1, p.g.nsplit));
-    return 0;
-  }
-  if (p.kernel == 5) {
-    snprintf(buf, cap, "conv_dec_tc(tcgen05 decode-at-use GEMM) CT=%d MT=%d GT=%d threads=%d smem=%zuB grid=%d NPOS=%d "
-             "chunks=%d tmemCols=%d", p.a.CT, p.a.MT, p.a.GT, p.threads, p.smem,
-             CeilDiv(N * p.a.IB, p.a.MT * 128) * p.a.G * p.a.nct, p.a.NPOS, p.a.NKC, p.a.tmemCols);
     return 0;
   }
   snprintf(buf, cap, "%s CPT=%d J=%d threads=%d smem=%zuB grid=(%d,%d) R=%d strips=%d CT=%d nct=%d PP=%d pwarps=%d "

@@ -347,22 +347,6 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   const int KS = 3;                 // k-steps per chunk (plane image of a chunk: 2 * 3 halves x NT images, hi + lo)
   const int NTq = std::min(256, RoundUp(N, 16));
   const int tilesq = CeilDiv(N, NTq), nChunksAll = CeilDiv(L->Din / 8, KS);
-  {
-    const size_t per = static_cast<size_t>(2 * KS) * NTq;
-    const size_t total = static_cast<size_t>(tilesq) * nChunksAll * per;
-    const size_t need = total * 2 * sizeof(float4);
-    if (need > L->flat_bytes) {
-      if (L->d_flat) QCNN_CUDA(cudaFree(L->d_flat));
-      L->d_flat = nullptr; L->flat_bytes = 0;
-      QCNN_CUDA(cudaMalloc(&L->d_flat, need));
-      L->ctx->alloc_epoch++;
-      L->flat_bytes = need;
-    }
-    fc_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, L->d_srcoff, reinterpret_cast<float4*>(L->d_flat),
-                                                                            N, L->Din, NTq, KS, nChunksAll, tilesq);
-    QCNN_CUDA(cudaGetLastError());
-    ctx->launches++;
-  }
   GemmArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = 2;
@@ -397,7 +381,24 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   a.nsplit = nsplit;
   a.dstRow = nsplit > 1 ? L->DoutPad : L->Dout;
   a.relu = nsplit > 1 ? 0 : relu;
-  if (PqGemmSmemBytes(a) > (ctx->smem_optin ? ctx->smem_optin : 227 * 1024)) return 0;
+  if (PqGemmSmemBytes(a) > (ctx->smem_optin ? ctx->smem_optin : 227 * 1024)) return 0;   // before any launch / allocation
+  {
+    const size_t per = static_cast<size_t>(2 * KS) * NTq;
+    const size_t total = static_cast<size_t>(tilesq) * nChunksAll * per;
+    const size_t need = total * 2 * sizeof(float4);
+    if (need > L->flat_bytes) {
+      if (L->d_flat) QCNN_CUDA(cudaFree(L->d_flat));
+      L->d_flat = nullptr; L->flat_bytes = 0;
+      QCNN_CUDA(cudaMalloc(&L->d_flat, need));
+      L->ctx->alloc_epoch++;
+      L->flat_bytes = need;
+    }
+    a.xprep = L->d_flat;
+    fc_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, L->d_srcoff, reinterpret_cast<float4*>(L->d_flat),
+                                                                            N, L->Din, NTq, KS, nChunksAll, tilesq);
+    QCNN_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
   if (nsplit > 1) {
     const size_t need = sizeof(float) * static_cast<size_t>(nsplit) * N * L->DoutPad;
     if (need > L->partial_bytes) {
@@ -409,7 +410,7 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
     }
     a.partial = L->d_partial;
   }
-  if (int rc = LaunchPqGemmArgs(a, static_cast<long long>(tiles) * nsplit * a.nct, st)) return rc;
+  if (int rc = LaunchPqGemmArgs(ctx, a, static_cast<long long>(tiles) * nsplit * a.nct, st)) return rc;
   ctx->launches++;
   if (nsplit > 1) {
     const int total = N * L->Dout;
@@ -426,6 +427,9 @@ int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaS
   QCNN_CHECK(N >= 1, "qcnn_fc_aprx_forward: N must be >= 1");
   {
     bool handled = false;
+    // batch <= 4: the persistent assignment-stream kernel (fc_chain.cu), here as a chain of one layer
+    if (int rc = LaunchFcChain(L->ctx, &L, &relu, 1, src, N, dst, st, nullptr, &handled)) return rc;
+    if (handled) return 0;
     if (int rc = LaunchFcTc(L, src, N, dst, relu, st, &handled)) return rc;
     if (handled) return 0;
   }

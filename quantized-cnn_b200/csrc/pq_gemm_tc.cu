@@ -415,7 +415,6 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         } else {
           MbarArrive(fullB + buf);
         }
-      } else if ((a.dbgSkip & 2) && kc >= 2) {
       } else {
 #pragma unroll
         for (int i = 0; i < kRegPos; i++) {
@@ -431,14 +430,14 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       if (a.mode != 2) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // planes are read by the tensor core
         MbarArrive(fullB + buf);
-        if (kc + 1 < nChunks && !((a.dbgSkip & 2) && kc >= 1)) loadPos(kc + 1);
+        if (kc + 1 < nChunks) loadPos(kc + 1);
       }
       if (kc + 2 < nChunks) {
         const int nb = (kc + 2) % kCbBufs;
         c0 = (DBG ? clock64() : 0ll);
         if (kc + 2 >= kCbBufs) MbarWait(emptyC + nb, (((kc + 2) / kCbBufs) - 1) & 1);
         sEC += (DBG ? clock64() : 0ll) - c0;
-        if ((a.dbgSkip & 2) && a.mode != 2) CpAsyncCommit(); else fetchChunk(kc + 2);
+        fetchChunk(kc + 2);
       }
     }
     if (DBG && a.dbg && st == 0) {
@@ -565,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
           int i0x[kMaxGT], i1x[kMaxGT];
 #pragma unroll
           for (int i = 0; i < kMaxGT; i++) {
-            if (i < n && !(a.dbgSkip & 1)) {
+            if (i < n) {
               const KStep ks = tabS[e0 + s0 + i];
               i0x[i] = ks.cb0 * K + (idb[ks.idx0 * 128] >> a.kshift);
               i1x[i] = ks.cb1 * K + (idb[ks.idx1 * 128] >> a.kshift);
@@ -574,10 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
           float4 w0[kMaxGT], w1[kMaxGT];
 #pragma unroll
           for (int i = 0; i < kMaxGT; i++) {
-            if (i < n) {
-              if (a.dbgSkip & 1) { w0[i] = make_float4(1.0f, 2.0f, 3.0f, 4.0f); w1[i] = w0[i]; }
-              else { w0[i] = cb[i0x[i]]; w1[i] = cb[i1x[i]]; }
-            }
+            if (i < n) { w0[i] = cb[i0x[i]]; w1[i] = cb[i1x[i]]; }
           }
 #pragma unroll
           for (int i = 0; i < kMaxGT; i++) {
@@ -647,9 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
 namespace qcnn {
 
 // Candidate tilings for batch N (cost in SM-cycles, comparable with PlanConv's model): 3 MMAs of NT/2 clk per k-step.
-// env QCNN_NO_DECTC=1 removes the family (the LUT + gather kernels remain).
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands) {
-  if (getenv("QCNN_NO_DECTC") != nullptr) return;
   const int G = L->grp, Cg = L->Cin / G, Kg = L->Cout / G, taps = L->ksz * L->ksz;
   if (L->K < 1 || L->K > 256 || Kg % 16 != 0) return;
   const size_t smemMax0 = L->ctx->smem_optin ? L->ctx->smem_optin : 227 * 1024;
@@ -774,6 +768,18 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
   }
 }
 
+// dynamic shared-memory limit of both instantiations: raised once per device to the opt-in maximum (not per launch,
+// which would make the limit follow whichever layer ran last -- fragile under graph capture / concurrent streams)
+static int SetSmemLimitOnce(qcnn_ctx* ctx) {
+  static bool done[64] = {false};
+  if (ctx->device >= 0 && ctx->device < 64 && done[ctx->device]) return 0;
+  const int lim = static_cast<int>(ctx->smem_optin ? ctx->smem_optin : 227 * 1024);
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  if (ctx->device >= 0 && ctx->device < 64) done[ctx->device] = true;
+  return 0;
+}
+
 int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st) {
   GemmArgs a = p.g;
   a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
@@ -799,11 +805,8 @@ int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, floa
     }
     a.partial = L->d_partial;
   }
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  if (int rc = SetSmemLimitOnce(L->ctx)) return rc;
   static const bool dbg = getenv("QCNN_GEMM_DBG") != nullptr;
-  static const int skip = getenv("QCNN_GEMM_SKIP") ? atoi(getenv("QCNN_GEMM_SKIP")) : 0;
-  a.dbgSkip = skip;
   if (dbg) {
     QCNN_CUDA(cudaMalloc(&a.dbg, 128));
     QCNN_CUDA(cudaMemsetAsync(a.dbg, 0, 128, st));
@@ -829,10 +832,10 @@ int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, floa
 
 // generic entry for callers that fill GemmArgs themselves (the fully-connected path in fc_aprx.cu)
 size_t PqGemmSmemBytes(const GemmArgs& a) { return static_cast<size_t>(MapSmem(a).total); }
-int LaunchPqGemmArgs(const GemmArgs& a, long long blocks, cudaStream_t st) {
+int LaunchPqGemmArgs(qcnn_ctx* ctx, const GemmArgs& a, long long blocks, cudaStream_t st) {
   const size_t smem = PqGemmSmemBytes(a);
   QCNN_CHECK(blocks >= 1 && blocks <= 2147483647LL, "pq_gemm_tc: bad grid");
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (int rc = SetSmemLimitOnce(ctx)) return rc;
   pq_gemm_tc_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(a);
   QCNN_CUDA(cudaGetLastError());
   return 0;

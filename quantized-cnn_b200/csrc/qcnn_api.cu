@@ -206,6 +206,7 @@ int qcnn_fc_layer_create(qcnn_ctx* ctx, int Din, int Dout, int S, int K, int d, 
 
 int qcnn_fc_layer_set_src_nhwc(qcnn_layer* L, int H, int W, int C) {
   QCNN_CHECK(L && L->kind == QCNN_KIND_FC, "qcnn_fc_layer_set_src_nhwc: not an FC layer");
+  L->ctx->alloc_epoch++;   // captured graphs may hold the old offset table / kernel choice
   if (L->d_srcoff) { cudaFree(L->d_srcoff); L->d_srcoff = nullptr; }
   if (H == 0 && W == 0 && C == 0) { L->src_h = L->src_w = L->src_c = 0; return 0; }
   QCNN_CHECK(H >= 1 && W >= 1 && C >= 1 && H * W * C == L->Din, "qcnn_fc_layer_set_src_nhwc: H*W*C=%d != Din=%d",
@@ -223,18 +224,29 @@ int qcnn_fc_layer_set_src_nhwc(qcnn_layer* L, int H, int W, int C) {
 int qcnn_conv_layer_set_src_nchw(qcnn_layer* L, int enable) {
   QCNN_CHECK(L && L->kind == QCNN_KIND_CONV, "qcnn_conv_layer_set_src_nchw: not a conv layer");
   QCNN_CHECK(!enable || L->stride > 1, "qcnn_conv_layer_set_src_nchw: only the strided kernel reads NCHW");
+  L->ctx->alloc_epoch++;
   L->src_nchw = enable ? 1 : 0;
   return 0;
 }
 
 int qcnn_layer_set_param(qcnn_layer* L, const char* name, int value) {
   QCNN_CHECK(L && name, "qcnn_layer_set_param: NULL argument");
+  L->ctx->alloc_epoch++;   // every parameter changes kernel choice or buffers: graphs captured before are stale
   if (!strcmp(name, "fc_nsplit")) L->opt_fc_nsplit = value;
   else if (!strcmp(name, "fc_tn")) L->opt_fc_tn = value;
   else if (!strcmp(name, "tensor_core")) {
     // 0: LUT + gather kernels only (fp32 adds in the reference's association; the strict-parity path);
     // 1 (default): large batches may use the decode-at-use tensor-core GEMMs (3xTF32, wider tolerance: DESIGN.md)
     L->opt_no_tc = value ? 0 : 1;
+    L->plan_N = 0; L->tuned = 0;
+    if (L->tunedPlans) L->tunedPlans->clear();
+  }
+  else if (!strcmp(name, "force_kernel") || !strcmp(name, "autotune")) {
+    // conv only.  force_kernel: -1 none, else 0 s1 | 1 roll | 2 s1_tc | 3 roll_tc | 4 direct | 6 pq_gemm_tc;
+    // autotune: 0 keeps the cost model's first tiling instead of timing the candidates on the device
+    QCNN_CHECK(L->kind == QCNN_KIND_CONV, "qcnn_layer_set_param: '%s' applies to conv layers", name);
+    if (name[0] == 'f') L->opt_force_kernel = value < 0 ? 0 : value + 1;
+    else L->opt_no_autotune = value ? 0 : 1;
     L->plan_N = 0; L->tuned = 0;
     if (L->tunedPlans) L->tunedPlans->clear();
   }
@@ -247,6 +259,10 @@ int qcnn_layer_describe(qcnn_layer* L, int N, char* buf, size_t cap) {
   if (L->kind == QCNN_KIND_CONV) return DescribeConv(L, N, buf, cap);
   char tc[256];
   DescribeFcTc(L, N, tc, sizeof(tc));
+  if (N <= 4) {
+    const int relu0 = 0;
+    DescribeFcChain(L->ctx, &L, &relu0, 1, tc, sizeof(tc));
+  }
   snprintf(buf, cap, "fc_aprx Din=%d Dout=%d S=%d K=%d d=%d%s%s", L->Din, L->Dout, L->S, L->K, L->d, tc[0] ? " via " : "", tc);
   return 0;
 }
@@ -258,6 +274,7 @@ void qcnn_layer_destroy(qcnn_layer* L) {
   if (L->d_bias) cudaFree(L->d_bias);
   if (L->d_partial) cudaFree(L->d_partial);
   if (L->d_flat) cudaFree(L->d_flat);
+  if (L->d_cpart) cudaFree(L->d_cpart);
   if (L->d_srcoff) cudaFree(L->d_srcoff);
   delete L->cands;
   delete L->tunedPlans;
@@ -334,21 +351,37 @@ int qcnn_layer_read_asmt_h(const qcnn_layer* L, uint8_t* out_h, size_t cap) {
 
 int qcnn_conv_aprx_forward(qcnn_layer* L, const float* src, int N, float* dst, int fuse_relu, void* stream) {
   QCNN_CHECK(L && src && dst, "qcnn_conv_aprx_forward: NULL argument");
+  QCNN_CUDA(cudaSetDevice(L->ctx->device));
   return LaunchConv(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
 }
 
 int qcnn_fc_aprx_forward(qcnn_layer* L, const float* src, int N, float* dst, int fuse_relu, void* stream) {
   QCNN_CHECK(L && src && dst, "qcnn_fc_aprx_forward: NULL argument");
+  QCNN_CUDA(cudaSetDevice(L->ctx->device));
   return LaunchFc(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
 }
 
 int qcnn_fc_aprx_forward_flat(qcnn_layer* L, const float* src, int N, float* dst, int fuse_relu, void* stream) {
   QCNN_CHECK(L && src && dst, "qcnn_fc_aprx_forward_flat: NULL argument");
+  QCNN_CUDA(cudaSetDevice(L->ctx->device));
   int* saved = L->d_srcoff;
   L->d_srcoff = nullptr;
   const int rc = LaunchFc(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
   L->d_srcoff = saved;
   return rc;
+}
+
+int qcnn_fc_chain_forward(qcnn_layer* const* layers, const int* relu, int n, const float* src, int N, float* dst,
+                          unsigned long long* stamps, void* stream) {
+  QCNN_CHECK(layers && relu && src && dst && n >= 1 && n <= 4, "qcnn_fc_chain_forward: bad argument (1..4 layers)");
+  for (int l = 0; l < n; l++) QCNN_CHECK(layers[l] && layers[l]->kind == QCNN_KIND_FC, "qcnn_fc_chain_forward: layer %d is not fully-connected", l);
+  QCNN_CHECK(N >= 1 && N <= 4, "qcnn_fc_chain_forward: N must be in [1, 4] (got %d)", N);
+  QCNN_CUDA(cudaSetDevice(layers[0]->ctx->device));
+  bool handled = false;
+  if (int rc = LaunchFcChain(layers[0]->ctx, layers, relu, n, src, N, dst, static_cast<cudaStream_t>(stream), stamps, &handled)) return rc;
+  QCNN_CHECK(handled, "qcnn_fc_chain_forward: these layers are not supported by the fused kernel (shape, shared memory, "
+             "fc_nsplit / fc_tn override, or QCNN_FC_CHAIN=0)");
+  return 0;
 }
 
 int qcnn_relu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, void* stream) {

@@ -78,13 +78,6 @@ struct ConvArgs {
   int pwarps, cwarps, rgroups;
   int ksplit;           // LUT build: K is split over ksplit thread groups
   int relu;
-  // decode-at-use tensor-core kernel (conv_dec_tc.cu): flat padded grid over the whole batch
-  int IB;               // flat positions per image = (Hi + pad) * PW
-  int MT;               // 128-position M tiles per CTA
-  int NPOS;             // input positions staged per CTA = MT*128 + halo (multiple of 8)
-  int GT;               // taps per weight-tile stage
-  int NKC;              // 8-channel chunks per group
-  int tmemCols;         // TMEM allocation (power of two >= MT*CT)
 };
 
 // ---- decode-at-use tensor-core GEMM (pq_gemm_tc.cu) ----
@@ -102,7 +95,6 @@ struct GemmArgs {
   const uint8_t* asmt;
   const float* bias;
   unsigned long long* dbg;    // optional cycle counters of the MMA issuer (QCNN_GEMM_DBG=1)
-  int dbgSkip;                // timing experiments only (QCNN_GEMM_SKIP): 1 decoders skip their loads, 2 stagers skip their work
   long long srcImg, dstImg;   // elements per source / destination image
   int N, Hi, Wi, Cin, Ho, Wo, Cout, ksz, pad, stride, G, Cg, Kg, KgPad, S, K, d;
   int mode;                   // 0 stride-1 conv, 1 strided conv on phase planes, 2 fully connected
@@ -130,7 +122,7 @@ struct GemmArgs {
 };
 
 struct ConvPlan {
-  int kernel;           // 0 s1, 1 roll, 2 s1_tc, 3 roll_tc, 4 direct, 5 dec_tc, 6 pq_gemm_tc (decode-at-use GEMMs on tcgen05)
+  int kernel;           // 0 s1, 1 roll, 2 s1_tc, 3 roll_tc, 4 direct, 6 pq_gemm_tc (decode-at-use GEMMs on tcgen05); 5 retired
   int CPT, J;
   int threads;
   size_t smem;
@@ -166,10 +158,14 @@ struct qcnn_layer {
   size_t partial_bytes;
   float* d_flat;         // tensor-core FC path: source pre-split into hi/lo plane images (fc_prep_kernel)
   size_t flat_bytes;
+  float* d_cpart;        // chain kernel (fc_chain.cu): per-CTA partial sums [sm_count][DoutPad], words double as ready flags
+  size_t cpart_bytes;
   // tuning overrides (0 = automatic)
   int opt_fc_nsplit;
   int opt_fc_tn;
   int opt_no_tc;         // 1: never use the decode-at-use tensor-core kernels for this layer
+  int opt_force_kernel;  // conv: 1 + kernel id the plan is restricted to (0 = none); tests pin the kernel they check
+  int opt_no_autotune;   // conv: 1 = keep the cost model's first tiling (no on-device timing)
 };
 
 namespace qcnn {
@@ -178,13 +174,15 @@ int PlanConv(qcnn_layer* L, int N);
 int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap);
 int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st);
 int LaunchFc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st);
-// conv_dec_tc.cu
-void PlanConvDec(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
-int LaunchConvDec(const ConvPlan& p, const ConvArgs& a, cudaStream_t st);
+// fc_chain.cu: one persistent launch for a run of consecutive FC layers at batch <= 4 (relu[l]: ReLU after layer l)
+bool FcChainEligible(qcnn_ctx* ctx, qcnn_layer* const* layers, const int* relu, int n, int N);
+void DescribeFcChain(qcnn_ctx* ctx, qcnn_layer* const* layers, const int* relu, int n, char* buf, size_t cap);
+int LaunchFcChain(qcnn_ctx* ctx, qcnn_layer* const* layers, const int* relu, int n, const float* src, int N, float* dst,
+                  cudaStream_t st, unsigned long long* dbg, bool* handled);
 // pq_gemm_tc.cu
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
 size_t PqGemmSmemBytes(const GemmArgs& a);
-int LaunchPqGemmArgs(const GemmArgs& a, long long blocks, cudaStream_t st);
+int LaunchPqGemmArgs(qcnn_ctx* ctx, const GemmArgs& a, long long blocks, cudaStream_t st);
 int LaunchSplitReduce(qcnn_ctx* ctx, const float* partial, float* dst, int rows, int cols, int colsPad, int nsplit, int relu,
                       cudaStream_t st);
 void DescribeFcTc(const qcnn_layer* L, int N, char* buf, size_t cap);

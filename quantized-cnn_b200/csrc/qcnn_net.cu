@@ -269,6 +269,7 @@ constexpr int kGraphMaxN = 8;
 int qcnn_net_forward(qcnn_net* net, const float* img, int N, float* prob, float* logits, void* stream) {
   QCNN_CHECK(net && img && prob, "qcnn_net_forward: NULL argument");
   QCNN_CHECK(N >= 1, "qcnn_net_forward: N must be >= 1");
+  QCNN_CUDA(cudaSetDevice(net->ctx->device));   // one process may drive several GPUs (qcnn_multi_*)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static const bool graphsOn = !(getenv("QCNN_GRAPH") && getenv("QCNN_GRAPH")[0] == '0');
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -366,6 +367,35 @@ static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, flo
     switch (type) {
       case QCNN_CONV:
       case QCNN_FCNT: {
+        if (type == QCNN_FCNT && !net->keep) {
+          // batch <= 4: the whole run FC [ReLU] [Drpt] FC ... as ONE persistent launch (fc_chain.cu)
+          qcnn_layer* chain[4];
+          int crelu[4];
+          int n = 0, j = l, outIdx = l;
+          while (j < L && net->layers[j].info.type == QCNN_FCNT && n < 4) {
+            chain[n] = net->layers[j].pq;
+            crelu[n] = 0;
+            j++;
+            if (j < L && net->layers[j].info.type == QCNN_RELU) { crelu[n] = 1; j++; }
+            n++;
+            outIdx = j;
+            int k = j;
+            while (k < L && net->layers[k].info.type == QCNN_DRPT) k++;   // identity at test time (CaffeEva.cc:1091-1096)
+            if (k < L && net->layers[k].info.type == QCNN_FCNT) j = k; else break;
+          }
+          if (n >= 1 && FcChainEligible(ctx, chain, crelu, n, N)) {
+            bool handled = false;
+            float* dst = net->maps[outIdx];
+            rc = LaunchFcChain(ctx, chain, crelu, n, cur, N, dst, st, nullptr, &handled);
+            if (rc) break;
+            if (handled) {
+              net->mapPtr[outIdx] = dst;
+              cur = dst;
+              l = outIdx;
+              break;
+            }
+          }
+        }
         const bool fuse = !net->keep && l + 1 < L && net->layers[l + 1].info.type == QCNN_RELU;
         const int outIdx = fuse ? l + 2 : l + 1;
         float* dst = net->maps[outIdx];

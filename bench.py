@@ -531,7 +531,7 @@ def run_b200_arm(args, q):
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
         fcs = [net.pq_layer(l) for l in (15, 18, 21)]
         xin = torch.rand((1, 9216), dtype=torch.float32, device=dev)
-        stamps = torch.zeros(2 * ctx.sm_count, dtype=torch.int64, device=dev)
+        stamps = torch.zeros(32 * ctx.sm_count, dtype=torch.int64, device=dev)
 
         def timed(fn, reps=12, use_stamps=True):
             ev, sp = [], []
@@ -545,7 +545,7 @@ def run_b200_arm(args, q):
                 if k >= 2:
                     ev.append(a.elapsed_time(b) * 1e3)
                     if use_stamps:
-                        st_ = stamps.cpu().numpy().reshape(-1, 2)
+                        st_ = stamps.cpu().numpy().reshape(-1, 32)
                         sp.append((st_[:, 1].max() - st_[:, 0].min()) / 1e3)
             return float(np.median(ev)), (float(np.median(sp)) if sp else None)
 

@@ -75,7 +75,10 @@ QCNN_API int qcnn_conv_layer_set_src_nchw(qcnn_layer* layer, int enable);
 /* tuning overrides for tests/benchmarks: "fc_nsplit" (subspace splits, 0 = automatic; 1 reproduces the reference's
  * accumulation order exactly), "fc_tn" (images per CTA: 1, 4 or 8; 0 = automatic), "tensor_core" (1 = default: large
  * batches may run as decode-at-use GEMMs on the tensor cores, 3xTF32; 0 = LUT + gather kernels only, the fp32
- * strict-parity path -- tolerances of both in DESIGN.md) */
+ * strict-parity path -- tolerances of both in DESIGN.md);
+ * conv layers, for tests that must know which kernel they check: "force_kernel" (-1 none | 0 s1 | 1 roll | 2 s1_tc |
+ * 3 roll_tc | 4 direct | 6 pq_gemm_tc), "gemm_nt" (positions per CTA of the pq_gemm_tc tilings, 0 = any), "autotune"
+ * (0 = keep the cost model's first tiling instead of timing the candidates of the chosen family on the device) */
 QCNN_API int qcnn_layer_set_param(qcnn_layer* layer, const char* name, int value);
 /* one-line description of the kernel + tiling chosen for batch N */
 QCNN_API int qcnn_layer_describe(qcnn_layer* layer, int N, char* buf, size_t cap);
@@ -106,8 +109,9 @@ QCNN_API int qcnn_fc_aprx_forward_flat(qcnn_layer* layer, const float* src, int 
  * CaffeEva::ExecForwardPass, src/CaffeEva.cc:213-261, each iteration being CalcFeatMap_FCntAprx :968-1025) as a single
  * persistent launch; batch <= 4 (the latency path, bound by the HBM stream of the assignment matrices).  relu[l] != 0
  * applies CalcFeatMap_ReLu after layer l.  src [N][Din of layers[0]] (or the NHWC map its set_src_nhwc folds),
- * dst [N][Dout of layers[n-1]].  stamps (nullable, device, 2 * sm_count u64): %globaltimer at the first / last
- * instruction of every CTA, for latency measurements.  Fails if the shapes are not supported by the fused kernel
+ * dst [N][Dout of layers[n-1]].  stamps (nullable, device, 32 * sm_count u64; per CTA: [0],[1] %globaltimer and [2],[3]
+ * clock64 at its first / last instruction, [4 + 5 l + i] clock64 after phase i of layer l: input slice, LUT, first
+ * assignment chunk landed, gather, publish), for latency measurements.  Fails if the shapes are not supported by the fused kernel
  * (qcnn_fc_aprx_forward per layer always works). */
 QCNN_API int qcnn_fc_chain_forward(qcnn_layer* const* layers, const int* relu, int n, const float* src, int N,
                                    float* dst, unsigned long long* stamps, void* stream);

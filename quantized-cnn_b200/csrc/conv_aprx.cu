@@ -1293,6 +1293,12 @@ int PlanConv(qcnn_layer* L, int N) {
   L->cands->clear();
   // layer parameter "force_kernel" / QCNN_FORCE_KERNEL=<0 s1 | 1 roll | 2 s1_tc | 3 roll_tc | 4 direct | 6 pq_gemm_tc>
   // restricts the choice (tests pin the kernel they check; fails when that kernel has no tiling for the layer)
+  if (L->opt_gemm_nt) {   // layer parameter "gemm_nt": only pq_gemm_tc tilings with that many positions per CTA
+    std::vector<std::pair<double, ConvPlan>> kept;
+    for (const auto& c : cands) if (c.second.kernel != 6 || c.second.g.NT == L->opt_gemm_nt) kept.push_back(c);
+    QCNN_CHECK(!kept.empty(), "qcnn_conv_aprx_forward: gemm_nt=%d has no tiling for this layer at batch %d", L->opt_gemm_nt, N);
+    cands.swap(kept);
+  }
   const char* force = getenv("QCNN_FORCE_KERNEL");
   if (L->opt_force_kernel || force) {
     const int want = L->opt_force_kernel ? L->opt_force_kernel - 1 : atoi(force);

@@ -25,6 +25,7 @@
 #include "qcnn_internal.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,26 +46,34 @@ struct ChainLayer {
   const float* ctrd;      // [S][K][d]
   const uint8_t* asmt;    // [S][DoutPad], stored byte = idx << kshift
   const float* bias;
-  const int* srcoff;      // first layer only: flattened feature -> source element offset (NULL: identity)
+  const int* srcoff;      // first layer only: flattened feature -> source element offset (NULL: identity / arithmetic fold)
   float* partial;         // [G][DoutPad]
   int Din, Dout, DoutPad, S, K, d;
+  int log2K;
   int pre;                // stored byte = byte offset inside a LUT row (K <= 64)
   int lutPitch;           // bytes per LUT row in shared memory (256 when pre, else 4 K)
   int unit, unitsBase, unitsRem;   // subspace split in units of `unit` rows
   int cpt, tpr, rg;       // channels per thread, threads per row, row groups
+  float tprInv;           // 1 / tpr (host-verified: floor((tid + 0.5) * tprInv) == tid / tpr for all consumer threads)
   int rpc;                // rows per ring chunk
   int relu;               // ReLU on this layer's output
   int ctrdOff;            // float offset of the codebook slice in shared memory
+  int srcHW, srcC;        // first layer reading an NHWC map: feature f = c * HW + pos lives at pos * C + c (0: not folded)
+  float srcHWInv;         // 1 / HW (host-verified like tprInv)
 };
 
 struct ChainArgs {
   ChainLayer L[kMaxChain];
   const float* src;
   float* dst;
-  unsigned long long* dbg;   // optional [2*G] globaltimer stamps (first / last instruction of every CTA)
+  unsigned long long* dbg;   // optional [G][32] stamps: [0],[1] %globaltimer at the CTA's first / last instruction; [2],[3] clock64
+                             // there; [4 + 5 l + i] clock64 after phase i of layer l (input slice, LUT, first chunk, gather, publish)
   int nLayers, G, nStage;
-  int xFloats, lutFloats, ctrdFloats, rgFloats, ringOff;
+  int cpcLast;               // output channels of the last layer reduced per CTA (multiple of 4)
+  int xFloats, lutFloats, ctrdFloats, rgFloats, scrFloats, ringOff;
 };
+
+static_assert(8 * (2 * kMaxStage + kMaxChain) <= kBarBytes, "shared-memory header layout");
 
 __device__ __forceinline__ uint32_t SmemU32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void MbarInit(uint64_t* b, int count) {
@@ -114,36 +123,81 @@ __device__ __forceinline__ void RowRange(const ChainLayer& L, int c, int* r0, in
   *r1 = min(L.S, (u0 + nu) * L.unit);
 }
 
-// sum over the G producing CTAs of partial[p][f .. f+3] (waits for every word, then resets it); the same value in all lanes
-__device__ __forceinline__ float4 CollectParts(float* partial, int pitch, int G, int f, int lane) {
-  constexpr int NP = kMaxParts / 32;
-  uint4 v[NP];
+// Cross-CTA reduction of a slice of a layer's output: sums[j] = sum over the G producing CTAs of partial[p][f0 + j],
+// j < 4 * ngroups (ngroups <= 16), by ALL consumer threads.  Returns (only in the threads with `*owner`) the sum of
+// feature *fc.
+//   pass 1  thread = (producer p, 4-float group g): consecutive lanes read consecutive 16-byte pieces of one producer's
+//           row, so a warp touches a few 128-byte lines per load (a lane-per-producer mapping costs 32 lines per load
+//           and blocks the load/store unit -- shared memory included -- for a microsecond).  Every word is polled
+//           until it is written, parked in shared memory [p][4 GP + 4], then reset (armed for the next call).
+//   pass 2  thread = (feature, chain c of 8): chain c adds producers c, c + 8, ... in ascending order, the eight chains
+//           are combined by a fixed shuffle tree: deterministic, no atomics.
+__device__ __forceinline__ float CollectSlice(float* partial, int pitch, int G, int f0, int ngroups, float* scr, int tid,
+                                              int* fc, bool* owner, unsigned long long* dbg) {
+  int log2GP = 0;
+  while ((1 << log2GP) < ngroups) log2GP++;
+  const int GP = 1 << log2GP, scrPitch = 4 * GP + 4;   // = 4 (mod 32) for GP >= 8: pass 2 is bank-conflict free
+  const int g = tid & (GP - 1), p0 = tid >> log2GP, pstep = kConsumers >> log2GP;
+  constexpr int NP = 5;    // passes over the producers: ceil(kMaxParts / (kConsumers / 16))
+  if (dbg) dbg[0] = clock64();
+  if (g < ngroups) {
+    float* base = partial + static_cast<size_t>(p0) * pitch + f0 + 4 * g;
+    const size_t dp = static_cast<size_t>(pstep) * pitch;
+    uint4 v[NP];
 #pragma unroll
-  for (int j = 0; j < NP; j++) {
-    const int p = lane + 32 * j;
-    if (p < G) v[j] = LdRelaxed4(partial + static_cast<size_t>(p) * pitch + f);
-    else v[j] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#pragma unroll
-  for (int j = 0; j < NP; j++) {
-    const int p = lane + 32 * j;
-    if (p < G) {
-      float* addr = partial + static_cast<size_t>(p) * pitch + f;
-      while (Pending(v[j])) v[j] = LdRelaxed4(addr);
-      *reinterpret_cast<uint4*>(addr) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);   // armed for the next call
-      s.x += __uint_as_float(v[j].x); s.y += __uint_as_float(v[j].y);
-      s.z += __uint_as_float(v[j].z); s.w += __uint_as_float(v[j].w);
+    for (int j = 0; j < NP; j++) {
+      if (p0 + j * pstep < G) v[j] = LdRelaxed4(base + j * dp);
+      else v[j] = make_uint4(0u, 0u, 0u, 0u);
     }
-  }
+    // words not written yet are polled again TOGETHER: one round trip after the slowest producer, not one per word
+    for (;;) {
+      bool pend = false;
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    s.x += __shfl_xor_sync(0xFFFFFFFFu, s.x, m);
-    s.y += __shfl_xor_sync(0xFFFFFFFFu, s.y, m);
-    s.z += __shfl_xor_sync(0xFFFFFFFFu, s.z, m);
-    s.w += __shfl_xor_sync(0xFFFFFFFFu, s.w, m);
+      for (int j = 0; j < NP; j++) pend = pend || Pending(v[j]);
+      if (!pend) break;
+#pragma unroll
+      for (int j = 0; j < NP; j++)
+        if (Pending(v[j])) v[j] = LdRelaxed4(base + j * dp);
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+      const int p = p0 + j * pstep;
+      if (p < G) *reinterpret_cast<uint4*>(scr + p * scrPitch + 4 * g) = v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++)      // armed for the next call (off the critical path: after the values are parked)
+      if (p0 + j * pstep < G) *reinterpret_cast<uint4*>(base + j * dp) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
   }
+  if (dbg) dbg[1] = clock64();
+  ConsumerSync();
+  const int f = tid >> 3, c = tid & 7;
+  float s = 0.0f;
+  if (f < 4 * ngroups) {
+    constexpr int NQ = kMaxParts / 8;
+    float t[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) t[q] = (c + 8 * q < G) ? scr[(c + 8 * q) * scrPitch + f] : 0.0f;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) s += t[q];      // producers c, c + 8, ... in ascending order (+0.0f past the last one)
+  }
+  s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
+  s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);
+  s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
+  if (dbg) dbg[2] = clock64();
+  *fc = f;
+  *owner = c == 0 && f < 4 * ngroups;
   return s;
+}
+
+// the 32-byte sectors CollectSlice will poll -- partial[p][f0 .. f0 + nf) of every producer p -- requested into L2 ahead of
+// time by the (otherwise idle) producer warp: after an L2 flush the first poll would go to DRAM and back while the
+// producers are already done
+__device__ __forceinline__ void PrefetchSlice(const float* partial, int pitch, int G, int f0, int nf, int lane) {
+  const int sectors = (nf + 7) >> 3;
+  for (int i = lane; i < G * sectors; i += 32) {
+    const int p = i / sectors, sct = i - p * sectors;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(partial + static_cast<size_t>(p) * pitch + f0 + 8 * sct));
+  }
 }
 
 template <int CPT> struct Idx;
@@ -154,52 +208,77 @@ __device__ __forceinline__ uint32_t IdxWord(const uint32_t& v, int) { return v; 
 __device__ __forceinline__ uint32_t IdxWord(const uint2& v, int i) { return i == 0 ? v.x : v.y; }
 __device__ __forceinline__ uint32_t IdxWord(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
+// not volatile: the compiler may schedule the lookups of several rows together (they only depend on the index words,
+// which are loaded after the chunk's mbarrier wait)
 __device__ __forceinline__ float LdShared(uint32_t addr) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
 
+// the CPT lookups of one assignment row.  PRE: the stored byte is already the byte offset inside a LUT row (K <= 64) and
+// LUT rows are 256-byte aligned, so ONE byte-permute both extracts the index and forms the shared-memory address:
+// 3 instructions per lookup (PRMT, LDS, FADD).
+template <int CPT, bool PRE, typename IV>
+__device__ __forceinline__ void GatherRow(const IV& w, uint32_t lr, float (&acc)[CPT]) {
+#pragma unroll
+  for (int c = 0; c < CPT; c++) {
+    uint32_t addr;
+    if (PRE) addr = __byte_perm(IdxWord(w, c >> 2), lr, 0x7650u | (c & 3));          // (lr & ~0xFF) | byte
+    else addr = lr + (__byte_perm(IdxWord(w, c >> 2), 0u, 0x4440u | (c & 3)) << 2);
+    acc[c] += LdShared(addr);
+  }
+}
+
 // Steps (3) and (4) of a layer for one consumer thread: gather-accumulate the CTA's assignment rows as their ring chunks
-// arrive (thread = CPT consecutive channels of the rows rgIdx, rgIdx + rg, ...), then publish the partial sums.
-// PRE: the stored byte is already the byte offset inside a LUT row (K <= 64) and LUT rows are 256-byte aligned, so ONE
-// byte-permute both extracts the index and forms the shared-memory address: 3 instructions per lookup (PRMT, LDS, FADD).
+// arrive (thread = CPT consecutive channels of the rows rgIdx, rgIdx + rg, ...; four rows are in flight together), then
+// publish the partial sums.
 template <int CPT, bool PRE>
 __device__ __forceinline__ void GatherAndPublish(const ChainLayer& L, int rows, int nStage, uint64_t* fullB, uint64_t* emptyB,
                                                  const uint8_t* ring, const float* lut, float* rgred, float* out, int tid,
-                                                 int lane, int* itp) {
+                                                 int lane, int* stagep, uint32_t* roundp, unsigned long long* dbg) {
   using IV = typename Idx<CPT>::type;
   float acc[CPT];
 #pragma unroll
   for (int c = 0; c < CPT; c++) acc[c] = 0.0f;
-  const int rgIdx = tid / L.tpr, cgIdx = tid - rgIdx * L.tpr;
+  const int rgIdx = __float2int_rd((static_cast<float>(tid) + 0.5f) * L.tprInv), cgIdx = tid - rgIdx * L.tpr;
   const bool active = rgIdx < L.rg;
   const int rowBytes = L.lutPitch, pitch = L.DoutPad, rg = L.rg;
   const uint32_t lutBase = SmemU32(lut);
-  int it = *itp;
-  for (int r = 0; r < rows; r += L.rpc, it++) {
-    const int stage = it % nStage;
-    MbarWait(fullB + stage, (it / nStage) & 1);
+  int stage = *stagep;
+  uint32_t round = *roundp;
+  for (int r = 0; r < rows; r += L.rpc) {
+    MbarWait(fullB + stage, round & 1u);
+    if (dbg && tid == 0 && r == 0) dbg[0] = clock64();
     if (active) {
       const uint8_t* chunk = ring + static_cast<size_t>(stage) * kChunkBytes + cgIdx * CPT;
       const int n = min(L.rpc, rows - r);
-#pragma unroll 4
-      for (int q = rgIdx; q < n; q += rg) {
-        const IV w = *reinterpret_cast<const IV*>(chunk + static_cast<size_t>(q) * pitch);
-        const uint32_t lr = lutBase + static_cast<uint32_t>(r + q) * rowBytes;
-#pragma unroll
-        for (int c = 0; c < CPT; c++) {
-          uint32_t addr;
-          if (PRE) addr = __byte_perm(IdxWord(w, c >> 2), lr, 0x7650u | (c & 3));          // (lr & ~0xFF) | byte
-          else addr = lr + (__byte_perm(IdxWord(w, c >> 2), 0u, 0x4440u | (c & 3)) << 2);
-          acc[c] += LdShared(addr);
-        }
+      const uint32_t lr0 = lutBase + static_cast<uint32_t>(r) * rowBytes;
+      int q = rgIdx;
+      for (; q + 3 * rg < n; q += 4 * rg) {
+        const uint8_t* p = chunk + static_cast<size_t>(q) * pitch;
+        const IV w0 = *reinterpret_cast<const IV*>(p);
+        const IV w1 = *reinterpret_cast<const IV*>(p + static_cast<size_t>(rg) * pitch);
+        const IV w2 = *reinterpret_cast<const IV*>(p + static_cast<size_t>(2 * rg) * pitch);
+        const IV w3 = *reinterpret_cast<const IV*>(p + static_cast<size_t>(3 * rg) * pitch);
+        const uint32_t lr = lr0 + static_cast<uint32_t>(q) * rowBytes, dl = static_cast<uint32_t>(rg) * rowBytes;
+        GatherRow<CPT, PRE>(w0, lr, acc);
+        GatherRow<CPT, PRE>(w1, lr + dl, acc);
+        GatherRow<CPT, PRE>(w2, lr + 2 * dl, acc);
+        GatherRow<CPT, PRE>(w3, lr + 3 * dl, acc);
+      }
+      for (; q < n; q += rg) {
+        const IV w0 = *reinterpret_cast<const IV*>(chunk + static_cast<size_t>(q) * pitch);
+        GatherRow<CPT, PRE>(w0, lr0 + static_cast<uint32_t>(q) * rowBytes, acc);
       }
     }
     __syncwarp();
     if (lane == 0) MbarArrive(emptyB + stage);
+    if (++stage == nStage) { stage = 0; round++; }
   }
-  *itp = it;
+  *stagep = stage;
+  *roundp = round;
+  if (dbg && tid == 0) dbg[1] = clock64();
   if (rg > 1) {
     if (active) {
       float* mine = rgred + static_cast<size_t>(rgIdx) * pitch + cgIdx * CPT;
@@ -220,6 +299,7 @@ __device__ __forceinline__ void GatherAndPublish(const ChainLayer& L, int rows, 
 #pragma unroll
     for (int c = 0; c < CPT; c += 4) StRelaxed4(o + c, acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
   }
+  if (dbg && tid == 0) dbg[2] = clock64();
 }
 
 __global__ void __launch_bounds__(kThreads, 1) fc_chain_kernel(const __grid_constant__ ChainArgs a) {
@@ -231,19 +311,22 @@ __global__ void __launch_bounds__(kThreads, 1) fc_chain_kernel(const __grid_cons
   float* lut = xs + a.xFloats;
   float* ctrdS = lut + a.lutFloats;
   float* rgred = ctrdS + a.ctrdFloats;
+  float* scr = rgred + a.rgFloats;
   uint8_t* ring = sm + a.ringOff;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cta = blockIdx.x;
-  if (a.dbg && tid == 0) a.dbg[2 * cta] = GlobalTimer();
-  if (tid == 0) {
-    for (int i = 0; i < a.nStage; i++) { MbarInit(fullB + i, 1); MbarInit(emptyB + i, kConsumerWarps); }
-    for (int l = 0; l < a.nLayers; l++) MbarInit(ctrdB + l, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (a.dbg && tid == 0) { a.dbg[32 * cta] = GlobalTimer(); a.dbg[32 * cta + 2] = clock64(); }
+  if (tid < a.nStage) { MbarInit(fullB + tid, 1); MbarInit(emptyB + tid, kConsumerWarps); }
+  if (tid >= 32 && tid < 32 + a.nLayers) MbarInit(ctrdB + (tid - 32), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // the argument block lives in the constant bank: touch every layer's lines now, together, instead of taking one cache
+  // miss (~0.2 us) on the critical path of each layer's first phase
+  if ((a.L[0].relu | a.L[1].relu | a.L[2].relu | a.L[3].relu | a.L[0].rpc | a.L[1].rpc | a.L[2].rpc | a.L[3].rpc) < 0) __trap();
   __syncthreads();
 
   if (warp == kConsumerWarps) {
     // ---- producer: codebook slices of every layer, then the assignment rows of every layer through the ring ----
+    int issued = 0;
     if (lane == 0) {
       for (int l = 0; l < a.nLayers; l++) {
         const ChainLayer& L = a.L[l];
@@ -255,17 +338,40 @@ __global__ void __launch_bounds__(kThreads, 1) fc_chain_kernel(const __grid_cons
           BulkLoad(ctrdS + L.ctrdOff, L.ctrd + static_cast<size_t>(r0) * L.K * L.d, bytes, ctrdB + l);
         }
       }
-      int it = 0;
+      int stage = 0;
+      uint32_t round = 0;
       for (int l = 0; l < a.nLayers; l++) {
         const ChainLayer& L = a.L[l];
         int r0, r1;
         RowRange(L, cta, &r0, &r1);
-        for (int r = r0; r < r1; r += L.rpc, it++) {
-          const int stage = it % a.nStage, round = it / a.nStage;
-          if (round > 0) MbarWait(emptyB + stage, (round - 1) & 1);
+        for (int r = r0; r < r1; r += L.rpc, issued++) {
+          if (round > 0) MbarWait(emptyB + stage, (round - 1) & 1u);
           const uint32_t bytes = static_cast<uint32_t>(min(L.rpc, r1 - r)) * L.DoutPad;
           MbarExpectTx(fullB + stage, bytes);
           BulkLoad(ring + static_cast<size_t>(stage) * kChunkBytes, L.asmt + static_cast<size_t>(r) * L.DoutPad, bytes, fullB + stage);
+          if (++stage == a.nStage) { stage = 0; round++; }
+        }
+      }
+    }
+    // every slice of partial sums this CTA will wait for, requested into L2 now (all lanes)
+    for (int l = 0; l < a.nLayers; l++) {
+      const ChainLayer& P = a.L[l];
+      if (l + 1 < a.nLayers) {
+        const ChainLayer& N = a.L[l + 1];
+        int r0, r1;
+        RowRange(N, cta, &r0, &r1);
+        PrefetchSlice(P.partial, P.DoutPad, a.G, r0 * N.d, min((r1 - r0) * N.d, max(0, N.Din - r0 * N.d)), lane);
+      } else {
+        const int o0 = cta * a.cpcLast;
+        PrefetchSlice(P.partial, P.DoutPad, a.G, o0, max(0, min(a.cpcLast, P.Dout - o0)), lane);
+      }
+    }
+    if (lane == 0) {
+      if (a.dbg) {   // measurement only: when the first 8 chunks landed ([24 + i]); valid while the ring is not recycled
+        a.dbg[32 * cta + 23] = clock64();   // all copies issued
+        for (int i = 0; i < min(issued, min(8, a.nStage)); i++) {
+          MbarWait(fullB + i, 0);
+          a.dbg[32 * cta + 24 + i] = clock64();
         }
       }
     }
@@ -273,7 +379,8 @@ __global__ void __launch_bounds__(kThreads, 1) fc_chain_kernel(const __grid_cons
   }
 
   // ---- consumers ----
-  int it = 0;
+  int stage = 0;
+  uint32_t round = 0;
   for (int l = 0; l < a.nLayers; l++) {
     const ChainLayer& L = a.L[l];
     int r0, r1;
@@ -284,35 +391,44 @@ __global__ void __launch_bounds__(kThreads, 1) fc_chain_kernel(const __grid_cons
     if (l == 0) {
       for (int i = tid; i < nf; i += kConsumers) {
         const int f = f0 + i;
-        xs[i] = f < L.Din ? __ldg(a.src + (L.srcoff ? __ldg(L.srcoff + f) : f)) : 0.0f;
+        int off = f;
+        if (L.srcHW) {          // NHWC map read in the reference's NCHW-flatten order (CaffeEva.cc:236-238)
+          const int c = __float2int_rd((static_cast<float>(f) + 0.5f) * L.srcHWInv);
+          off = (f - c * L.srcHW) * L.srcC + c;
+        } else if (L.srcoff && f < L.Din) {
+          off = __ldg(L.srcoff + f);
+        }
+        xs[i] = f < L.Din ? __ldg(a.src + off) : 0.0f;
       }
     } else {
+      // sum of the previous layer's per-CTA partial sums (+ bias, ReLU) for this CTA's input features only
       const ChainLayer& P = a.L[l - 1];
-      const int groups = (nf + 3) >> 2;
-      for (int g = warp; g < groups; g += kConsumerWarps) {
-        const int f = f0 + 4 * g;
-        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (f < L.Din) {   // Din == P.Dout <= P.DoutPad (multiple of 16): the whole group lies inside a partial row
-          v = CollectParts(P.partial, P.DoutPad, a.G, f, lane);
-          float o[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            o[j] = (f + j < L.Din) ? o[j] + __ldg(P.bias + f + j) : 0.0f;
-            if (P.relu) o[j] = fmaxf(o[j], 0.0f);
-          }
-          v = make_float4(o[0], o[1], o[2], o[3]);
+      const int groups = (min(nf, max(0, L.Din - f0)) + 3) >> 2;   // Din == P.Dout <= P.DoutPad (multiple of 16)
+      for (int i = 4 * groups + tid; i < nf; i += kConsumers) xs[i] = 0.0f;
+      for (int b = 0; b < groups; b += 16) {
+        if (b) ConsumerSync();      // the scratch of the previous batch has been read
+        int fc;
+        bool owner;
+        const int fb = f0 + 4 * b + (tid >> 3);         // the feature this thread will own: its bias is fetched meanwhile
+        const float bv = (fb < L.Din) ? __ldg(P.bias + fb) : 0.0f;
+        const float v = CollectSlice(P.partial, P.DoutPad, a.G, f0 + 4 * b, min(16, groups - b), scr, tid, &fc, &owner, nullptr);
+        if (owner) {
+          const int f = f0 + 4 * b + fc;
+          float o = f < L.Din ? v + bv : 0.0f;
+          if (P.relu) o = fmaxf(o, 0.0f);
+          xs[4 * b + fc] = o;
         }
-        if (lane == 0) *reinterpret_cast<float4*>(xs + 4 * g) = v;
       }
     }
     ConsumerSync();
+    if (a.dbg && tid == 0) a.dbg[32 * cta + 4 + 5 * l] = clock64();
     // (2) LUT rows of the CTA's subspaces (reference GetInPdMat: ascending j, separate multiply and add)
     if (rows > 0) {
       MbarWait(ctrdB + l, 0);
       const float* cs = ctrdS + L.ctrdOff;
-      const int d = L.d;
+      const int d = L.d, kmask = L.K - 1, lutRowF = L.lutPitch >> 2;
       for (int e = tid; e < rows * L.K; e += kConsumers) {
-        const int r = e / L.K;
+        const int r = e >> L.log2K;
         const int dims = min(d, L.Din - (r0 + r) * d);
         const float* c = cs + static_cast<size_t>(e) * d;
         const float* x = xs + r * d;
@@ -327,13 +443,15 @@ __global__ void __launch_bounds__(kThreads, 1) fc_chain_kernel(const __grid_cons
         } else {
           for (int j = 0; j < dims; j++) v = __fadd_rn(v, __fmul_rn(x[j], c[j]));
         }
-        lut[r * (L.lutPitch >> 2) + (e - r * L.K)] = v;
+        lut[r * lutRowF + (e & kmask)] = v;
       }
     }
     ConsumerSync();
+    if (a.dbg && tid == 0) a.dbg[32 * cta + 5 + 5 * l] = clock64();
     // (3) + (4) gather-accumulate the assignment rows as they arrive, publish the partial sums of all DoutPad channels
     float* out = L.partial + static_cast<size_t>(cta) * L.DoutPad;
-#define QCNN_GP(C, P) GatherAndPublish<C, P>(L, rows, a.nStage, fullB, emptyB, ring, lut, rgred, out, tid, lane, &it)
+#define QCNN_GP(C, P) GatherAndPublish<C, P>(L, rows, a.nStage, fullB, emptyB, ring, lut, rgred, out, tid, lane, &stage, &round, \
+                                             a.dbg ? a.dbg + 32 * cta + 6 + 5 * l : nullptr)
     if (L.pre) { if (L.cpt == 8) QCNN_GP(8, true); else if (L.cpt == 4) QCNN_GP(4, true); else QCNN_GP(16, true); }
     else { if (L.cpt == 8) QCNN_GP(8, false); else if (L.cpt == 4) QCNN_GP(4, false); else QCNN_GP(16, false); }
 #undef QCNN_GP
@@ -342,22 +460,24 @@ __global__ void __launch_bounds__(kThreads, 1) fc_chain_kernel(const __grid_cons
   // ---- output of the last layer: a multiple of four channels per CTA ----
   {
     const ChainLayer& P = a.L[a.nLayers - 1];
-    const int cpc = ((P.Dout + a.G - 1) / a.G + 3) & ~3;
-    const int o0 = cta * cpc;
-    const int n = max(0, min(cpc, P.Dout - o0));
-    for (int g = warp; g < ((n + 3) >> 2); g += kConsumerWarps) {
-      const int o = o0 + 4 * g;
-      const float4 v = CollectParts(P.partial, P.DoutPad, a.G, o, lane);
-      if (lane == 0) {
-        const float r[4] = {v.x, v.y, v.z, v.w};
-        for (int j = 0; j < 4 && o + j < P.Dout; j++) {
-          const float t = r[j] + __ldg(P.bias + o + j);
-          a.dst[o + j] = P.relu ? fmaxf(t, 0.0f) : t;
-        }
+    const int o0 = cta * a.cpcLast;
+    const int groups = (max(0, min(a.cpcLast, P.Dout - o0)) + 3) >> 2;
+    for (int b = 0; b < groups; b += 16) {
+      if (b) ConsumerSync();   // the scratch of the previous batch has been read (its last use before: many barriers ago)
+      int fc;
+      bool owner;
+      const int ob = o0 + 4 * b + (tid >> 3);
+      const float bv = (ob < P.Dout) ? __ldg(P.bias + ob) : 0.0f;
+      const float v = CollectSlice(P.partial, P.DoutPad, a.G, o0 + 4 * b, min(16, groups - b), scr, tid, &fc, &owner,
+                                   (a.dbg && tid == 0 && b == 0) ? a.dbg + 32 * cta + 19 : nullptr);
+      const int o = o0 + 4 * b + fc;
+      if (owner && o < P.Dout) {
+        const float t = v + bv;
+        a.dst[o] = P.relu ? fmaxf(t, 0.0f) : t;
       }
     }
   }
-  if (a.dbg && tid == 0) a.dbg[2 * cta + 1] = GlobalTimer();
+  if (a.dbg && tid == 0) { a.dbg[32 * cta + 1] = GlobalTimer(); a.dbg[32 * cta + 3] = clock64(); }
 }
 
 int Gcd(int a, int b) { return b ? Gcd(b, a % b) : a; }
@@ -392,6 +512,9 @@ static bool PlanChain(qcnn_ctx* ctx, qcnn_layer* const* layers, const int* relu,
     ChainLayer& L = a.L[l];
     L.ctrd = Q->d_ctrd; L.asmt = Q->d_asmt; L.bias = Q->d_bias; L.srcoff = Q->d_srcoff; L.partial = Q->d_cpart;
     L.Din = Q->Din; L.Dout = Q->Dout; L.DoutPad = Q->DoutPad; L.S = Q->S; L.K = Q->K; L.d = Q->d;
+    L.log2K = 0;
+    while ((1 << L.log2K) < Q->K) L.log2K++;
+    if ((1 << L.log2K) != Q->K) return false;
     L.pre = Q->kshift == 2 ? 1 : 0;
     L.lutPitch = L.pre ? 256 : Q->K * 4;
     L.relu = relu[l];
@@ -399,6 +522,16 @@ static bool PlanChain(qcnn_ctx* ctx, qcnn_layer* const* layers, const int* relu,
     if (Q->DoutPad / L.cpt > kConsumers) return false;
     L.tpr = Q->DoutPad / L.cpt;
     L.rg = std::min(kConsumers / L.tpr, 16);
+    L.tprInv = 1.0f / static_cast<float>(L.tpr);
+    for (int t = 0; t < kConsumers; t++)     // the kernel divides by multiplying: must be exact for every thread index
+      if (static_cast<int>(floorf((static_cast<float>(t) + 0.5f) * L.tprInv)) != t / L.tpr) return false;
+    if (Q->src_h > 0 && l == 0) {            // NHWC fold by arithmetic (same check); otherwise the offset table is used
+      const int hw = Q->src_h * Q->src_w;
+      const float inv = 1.0f / static_cast<float>(hw);
+      bool exact = true;
+      for (int f = 0; f < Q->Din && exact; f++) exact = static_cast<int>(floorf((static_cast<float>(f) + 0.5f) * inv)) == f / hw;
+      if (exact) { L.srcHW = hw; L.srcC = Q->src_c; L.srcHWInv = inv; }
+    }
     L.rpc = std::max(1, kChunkBytes / Q->DoutPad);
     L.unit = 4 / Gcd(Q->d, 4);
     const int units = CeilDiv(Q->S, L.unit);
@@ -410,8 +543,18 @@ static bool PlanChain(qcnn_ctx* ctx, qcnn_layer* const* layers, const int* relu,
     lutF = std::max(lutF, RoundUp(rowsMax * (L.lutPitch / 4), 64));
     if (L.rg > 1) rgF = std::max(rgF, L.rg * Q->DoutPad);
   }
+  a.cpcLast = RoundUp(CeilDiv(layers[n - 1]->Dout, G), 4);
+  // scratch of the cross-CTA reduction: [G][4 GP + 4] floats, GP = groups of 4 features reduced together (<= 16)
+  int gmax = std::min(16, a.cpcLast / 4);
+  for (int l = 1; l < n; l++) {
+    const int rowsMax = std::min(a.L[l].S, (a.L[l].unitsBase + (a.L[l].unitsRem ? 1 : 0)) * a.L[l].unit);
+    gmax = std::max(gmax, std::min(16, CeilDiv(rowsMax * a.L[l].d, 4)));
+  }
+  int gp = 1;
+  while (gp < gmax) gp *= 2;
+  a.scrFloats = G * (4 * gp + 4);
   a.xFloats = xF; a.lutFloats = lutF; a.ctrdFloats = ctrdF; a.rgFloats = rgF;
-  const size_t fixed = kBarBytes + sizeof(float) * (static_cast<size_t>(xF) + lutF + ctrdF + rgF);
+  const size_t fixed = kBarBytes + sizeof(float) * (static_cast<size_t>(xF) + lutF + ctrdF + rgF + a.scrFloats);
   a.ringOff = static_cast<int>((fixed + 127) & ~static_cast<size_t>(127));
   const size_t cap = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
   if (static_cast<size_t>(a.ringOff) + 2 * kChunkBytes > cap) return false;

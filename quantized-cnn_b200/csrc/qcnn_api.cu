@@ -241,11 +241,13 @@ int qcnn_layer_set_param(qcnn_layer* L, const char* name, int value) {
     L->plan_N = 0; L->tuned = 0;
     if (L->tunedPlans) L->tunedPlans->clear();
   }
-  else if (!strcmp(name, "force_kernel") || !strcmp(name, "autotune")) {
+  else if (!strcmp(name, "force_kernel") || !strcmp(name, "autotune") || !strcmp(name, "gemm_nt")) {
     // conv only.  force_kernel: -1 none, else 0 s1 | 1 roll | 2 s1_tc | 3 roll_tc | 4 direct | 6 pq_gemm_tc;
-    // autotune: 0 keeps the cost model's first tiling instead of timing the candidates on the device
+    // autotune: 0 keeps the cost model's first tiling instead of timing the candidates on the device;
+    // gemm_nt: positions per CTA of the pq_gemm_tc tilings (0 = any; 256 = one TMEM accumulator, <= 128 = two)
     QCNN_CHECK(L->kind == QCNN_KIND_CONV, "qcnn_layer_set_param: '%s' applies to conv layers", name);
     if (name[0] == 'f') L->opt_force_kernel = value < 0 ? 0 : value + 1;
+    else if (name[0] == 'g') L->opt_gemm_nt = value < 0 ? 0 : value;
     else L->opt_no_autotune = value ? 0 : 1;
     L->plan_N = 0; L->tuned = 0;
     if (L->tunedPlans) L->tunedPlans->clear();

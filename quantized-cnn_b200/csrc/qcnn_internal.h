@@ -166,6 +166,7 @@ struct qcnn_layer {
   int opt_no_tc;         // 1: never use the decode-at-use tensor-core kernels for this layer
   int opt_force_kernel;  // conv: 1 + kernel id the plan is restricted to (0 = none); tests pin the kernel they check
   int opt_no_autotune;   // conv: 1 = keep the cost model's first tiling (no on-device timing)
+  int opt_gemm_nt;       // conv: restrict pq_gemm_tc tilings to this many positions per CTA (0 = any)
 };
 
 namespace qcnn {

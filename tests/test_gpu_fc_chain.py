@@ -97,10 +97,10 @@ def test_fc_chain_nhwc_source_and_stamps(po, qcnn, ctx):
     l1.set_src_nhwc(H, W, Cc)
     x = rand_act(rng, (2, H, W, Cc), scale=1.0)
     ref = ref_chain(po, po.nhwc_to_nchw(x).reshape(2, -1), [p1, p2], [1, 0])
-    stamps = torch.zeros(2 * ctx.sm_count, dtype=torch.int64, device="cuda")
+    stamps = torch.zeros(32 * ctx.sm_count, dtype=torch.int64, device="cuda")
     y = qcnn.fc_chain_forward([l1, l2], [1, 0], torch.from_numpy(x).cuda().view(2, -1), stamps=stamps).cpu().numpy()
     assert close(y, ref) <= RTOL, close(y, ref)
-    st = stamps.cpu().numpy().reshape(-1, 2)
+    st = stamps.cpu().numpy().reshape(-1, 32)
     assert (st[:, 0] > 0).all() and (st[:, 1] > st[:, 0]).all()
     span_us = (st[:, 1].max() - st[:, 0].min()) / 1e3
     assert span_us < 1000.0      # sanity: one launch of the second image, microseconds

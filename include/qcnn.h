@@ -146,6 +146,19 @@ QCNN_API int qcnn_net_create(qcnn_ctx* ctx, const char* model_name, const char* 
                              qcnn_net** out);
 QCNN_API int qcnn_net_create_custom(qcnn_ctx* ctx, int layer_cnt, const qcnn_layer_info* layers, int img_chn,
                                     int img_hei, int img_wid, const char* dir, const char* pfx, qcnn_net** out);
+/* Same, from parameters the caller already holds in host memory -- what CaffeEva::LoadCaffePara has after
+ * CaffePara::LoadLayerPara (src/CaffeEva.cc:134-139): one record per layer == the reference's LayerPara
+ * (include/CaffePara.h:45-58) restricted to the PQ members; all pointers NULL for layers without parameters.
+ *   ctrd [S][K][d] f32 (ctrdLst), asmt u8 0-based ([Cout][k][k][S] conv / [Dout][S] FC, asmtLst), bias f32 (biasVec) */
+typedef struct {
+  const float* ctrd;
+  const uint8_t* asmt;
+  const float* bias;
+  int S, K, d;
+} qcnn_layer_para;
+QCNN_API int qcnn_net_create_from_para(qcnn_ctx* ctx, int layer_cnt, const qcnn_layer_info* layers,
+                                       const qcnn_layer_para* para, int img_chn, int img_hei, int img_wid,
+                                       qcnn_net** out);
 QCNN_API void qcnn_net_destroy(qcnn_net* net);
 QCNN_API int qcnn_net_layer_count(const qcnn_net* net);
 QCNN_API int qcnn_net_out_len(const qcnn_net* net);
@@ -171,6 +184,35 @@ QCNN_API int qcnn_net_layer_work(qcnn_net* net, int layer, int N, double* alg_by
 QCNN_API int qcnn_net_launch_count(const qcnn_net* net);
 /* PQ layer handle of layer `l` (NULL for non-PQ layers); owned by the net */
 QCNN_API qcnn_layer* qcnn_net_pq_layer(qcnn_net* net, int l);
+
+/* ---- multi-GPU: ONE process drives n_dev GPUs of a box -----------------------------------------
+ * The batch is sharded by image (rank r owns rows [r*per, min(N, (r+1)*per)), per = ceil(N / n_dev)), the weights are
+ * replicated, and the only exchange is one ncclAllGather of the per-rank probabilities over NVLink, after which every
+ * GPU holds the [N][out_len] result -- what CaffeEva::ExecForwardPass (src/CaffeEva.cc:213-261) leaves in
+ * featMapLst[layerCnt].  devices == NULL means 0 .. n_dev-1.  NCCL is loaded at run time (libnccl.so.2); the calls fail
+ * if it is missing (no host-staged fallback). */
+typedef struct qcnn_multi qcnn_multi;
+QCNN_API int qcnn_multi_create(int n_dev, const int* devices, const char* model_name, const char* dir, const char* pfx,
+                               qcnn_multi** out);
+QCNN_API int qcnn_multi_create_from_para(int n_dev, const int* devices, int layer_cnt, const qcnn_layer_info* layers,
+                                         const qcnn_layer_para* para, int img_chn, int img_hei, int img_wid,
+                                         qcnn_multi** out);
+QCNN_API void qcnn_multi_destroy(qcnn_multi* m);
+QCNN_API int qcnn_multi_device_count(const qcnn_multi* m);
+QCNN_API int qcnn_multi_out_len(const qcnn_multi* m);
+QCNN_API int qcnn_multi_nccl_version(const qcnn_multi* m);
+/* the replica of rank `rank` (owned by m): for qcnn_net_pq_layer / qcnn_layer_set_param on every replica */
+QCNN_API qcnn_net* qcnn_multi_net(qcnn_multi* m, int rank);
+/* == CaffeEva::ExecForwardPass(imgDataIn, pProbVecOut) on n_dev GPUs: img_h [N][C][H][W] host (pinned for concurrent
+ * copies), prob_h [N][out_len] host; shards go up on every GPU's own link, forward, all-gather, rank 0's copy comes
+ * back; synchronises. */
+QCNN_API int qcnn_multi_forward_h(qcnn_multi* m, const float* img_h, int N, float* prob_h);
+/* device-resident, asynchronous step: img_dev[r] = rank r's shard on device r; prob_all_dev[r] (nullable array) receives
+ * the device-r pointer of the gathered [N][out_len] probabilities (library-owned, valid until the step after next).  The
+ * all-gather runs on a side stream, so consecutive steps overlap it with the next step's layers; qcnn_multi_sync waits
+ * for everything issued. */
+QCNN_API int qcnn_multi_forward(qcnn_multi* m, const float* const* img_dev, int N, const float** prob_all_dev);
+QCNN_API int qcnn_multi_sync(qcnn_multi* m);
 
 /* ---- file formats (include/FileIO.h:56-178, 229-350), host only ------------------------------------------- */
 /* .bin: returns element count or -1; dims4 padded with 1; data_h may be NULL to query the shape */

@@ -86,6 +86,7 @@ _SIGS = {
     "qcnn_nhwc_to_nchw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "qcnn_net_create": (_i, [_vp, _cp, _cp, _cp, C.POINTER(_vp)]),
     "qcnn_net_create_custom": (_i, [_vp, _i, C.POINTER(LayerInfo), _i, _i, _i, _cp, _cp, C.POINTER(_vp)]),
+    "qcnn_net_create_from_para": (_i, [_vp, _i, C.POINTER(LayerInfo), _vp, _i, _i, _i, C.POINTER(_vp)]),
     "qcnn_net_destroy": (None, [_vp]),
     "qcnn_net_layer_count": (_i, [_vp]),
     "qcnn_net_out_len": (_i, [_vp]),
@@ -99,6 +100,16 @@ _SIGS = {
     "qcnn_net_layer_work": (_i, [_vp, _i, _i, _dp, _dp, _dp]),
     "qcnn_net_launch_count": (_i, [_vp]),
     "qcnn_net_pq_layer": (_vp, [_vp, _i]),
+    "qcnn_multi_create": (_i, [_i, C.POINTER(_i), _cp, _cp, _cp, C.POINTER(_vp)]),
+    "qcnn_multi_create_from_para": (_i, [_i, C.POINTER(_i), _i, C.POINTER(LayerInfo), _vp, _i, _i, _i, C.POINTER(_vp)]),
+    "qcnn_multi_destroy": (None, [_vp]),
+    "qcnn_multi_device_count": (_i, [_vp]),
+    "qcnn_multi_out_len": (_i, [_vp]),
+    "qcnn_multi_nccl_version": (_i, [_vp]),
+    "qcnn_multi_net": (_vp, [_vp, _i]),
+    "qcnn_multi_forward_h": (_i, [_vp, _vp, _i, _vp]),
+    "qcnn_multi_forward": (_i, [_vp, C.POINTER(_vp), _i, C.POINTER(_vp)]),
+    "qcnn_multi_sync": (_i, [_vp]),
     "qcnn_read_bin_f32": (C.c_long, [_cp, C.POINTER(_i), C.POINTER(_i), _vp, C.c_long]),
     "qcnn_write_bin_f32": (_i, [_cp, _i, C.POINTER(_i), _vp]),
     "qcnn_read_cbn_u8": (C.c_long, [_cp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _vp, C.c_long]),
@@ -390,6 +401,66 @@ class Net(object):
     def pq_layer(self, l):
         h = lib.qcnn_net_pq_layer(self.h, l)
         return _Layer(self.ctx, _vp(h), owned=False) if h else None
+
+
+class MultiNet(object):
+    """One process, several GPUs: batch-sharded replicas + NCCL all-gather of the probabilities (qcnn_multi_*)."""
+
+    def __init__(self, dirpath, pfx, model="AlexNet", devices=(0,)):
+        devices = list(devices)
+        arr = (_i * len(devices))(*devices)
+        h = _vp()
+        _check(lib.qcnn_multi_create(len(devices), arr, model.encode(), dirpath.encode(), pfx.encode(), C.byref(h)))
+        self.h, self.devices = h, devices
+        self.out_len = lib.qcnn_multi_out_len(h)
+
+    def close(self):
+        if self.h:
+            lib.qcnn_multi_destroy(self.h)
+            self.h = None
+
+    @property
+    def nccl_version(self):
+        return lib.qcnn_multi_nccl_version(self.h)
+
+    def pq_layer(self, rank, l):
+        net = lib.qcnn_multi_net(self.h, rank)
+        h = lib.qcnn_net_pq_layer(net, l)
+        return _Layer(None, _vp(h), owned=False) if h else None
+
+    def forward_host(self, img_h, prob_h=None):
+        def ptr(a):
+            return C.c_void_p(a.data_ptr()) if hasattr(a, "data_ptr") else a.ctypes.data_as(_vp)
+        N = img_h.shape[0]
+        if prob_h is None:
+            prob_h = np.empty((N, self.out_len), np.float32)
+        _check(lib.qcnn_multi_forward_h(self.h, ptr(img_h), N, ptr(prob_h)))
+        return prob_h
+
+    def shard(self, N, r):
+        per = -(-N // len(self.devices))
+        return min(N, r * per), min(N, (r + 1) * per)
+
+    def forward(self, shards, N):
+        """shards[r]: CUDA float32 tensor on device r with rank r's images; returns device pointers of the gathered probs."""
+        R = len(self.devices)
+        ins = (_vp * R)(*[(_dptr(t).value if t is not None else None) for t in shards])
+        outs = (_vp * R)()
+        _check(lib.qcnn_multi_forward(self.h, ins, N, outs))
+        return [outs[r] for r in range(R)]
+
+    def sync(self):
+        _check(lib.qcnn_multi_sync(self.h))
+
+    def gathered(self, ptr, N, rank):
+        """torch view [N, out_len] of a gathered buffer returned by forward() (after sync)."""
+        import torch
+
+        class _View(object):
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = dict(shape=(N, self.out_len), typestr="<f4", data=(int(ptr), False), version=2)
+        return torch.as_tensor(v, device="cuda:%d" % self.devices[rank])
 
 
 # ---- file formats (host) ----------------------------------------------------------------------------------

@@ -525,7 +525,8 @@ static bool PlanChain(qcnn_ctx* ctx, qcnn_layer* const* layers, const int* relu,
     L.tprInv = 1.0f / static_cast<float>(L.tpr);
     for (int t = 0; t < kConsumers; t++)     // the kernel divides by multiplying: must be exact for every thread index
       if (static_cast<int>(floorf((static_cast<float>(t) + 0.5f) * L.tprInv)) != t / L.tpr) return false;
-    if (Q->src_h > 0 && l == 0) {            // NHWC fold by arithmetic (same check); otherwise the offset table is used
+    if (Q->d_srcoff && Q->src_h > 0 && l == 0) {   // NHWC fold by arithmetic (same check); otherwise the offset table is used
+                                                   // (d_srcoff is NULL while qcnn_fc_aprx_forward_flat passes a flat vector)
       const int hw = Q->src_h * Q->src_w;
       const float inv = 1.0f / static_cast<float>(hw);
       bool exact = true;

@@ -81,64 +81,47 @@ static int EnsureCapacity(qcnn_net* net, int N) {
   return 0;
 }
 
-static int BuildNet(qcnn_ctx* ctx, CaffePara& para, qcnn_net** out) {
+static int BuildNet(qcnn_ctx* ctx, int layerCnt, const qcnn_layer_info* infos, const qcnn_layer_para* paras, int imgC, int imgH,
+                    int imgW, qcnn_net** out) {
   qcnn_net* net = new qcnn_net();
   net->ctx = ctx;
-  net->imgC = para.imgChnIn; net->imgH = para.imgHeiIn; net->imgW = para.imgWidIn;
+  net->imgC = imgC; net->imgH = imgH; net->imgW = imgW;
   net->keep = 0; net->profiling = 0; net->capN = 0; net->lastLaunches = 0;
   net->d_in[0] = net->d_in[1] = nullptr; net->d_in_cap = 0;
   net->d_prob = net->d_logit = nullptr; net->d_out_cap = 0;
   net->stCopy = net->stComp = nullptr;
   net->chunk = 64;
-  int H = para.imgHeiIn, W = para.imgWidIn, C = para.imgChnIn;
+  int H = imgH, W = imgW, C = imgC;
   bool seenFc = false;
   int rc = 0;
-  for (int l = 0; l < para.layerCnt && rc == 0; l++) {
-    const LayerInfo& li = para.layerInfoLst[l];
+  for (int l = 0; l < layerCnt && rc == 0; l++) {
     NetLayer nl;
     memset(&nl, 0, sizeof(nl));
-    nl.info.type = static_cast<int>(li.type);
-    nl.info.padSiz = li.padSiz; nl.info.knlSiz = li.knlSiz; nl.info.knlCnt = li.knlCnt; nl.info.grpCnt = li.grpCnt;
-    nl.info.stride = li.stride; nl.info.nodCnt = li.nodCnt; nl.info.lrnSiz = li.lrnSiz; nl.info.lrnAlp = li.lrnAlp;
-    nl.info.lrnBet = li.lrnBet; nl.info.lrnIni = li.lrnIni; nl.info.drpRat = li.drpRat;
+    nl.info = infos[l];
+    const qcnn_layer_info& li = nl.info;
     nl.Hin = H; nl.Win = W; nl.Cin = C;
-    const LayerPara& lp = para.layerParaLst[l];
+    const qcnn_layer_para& lp = paras[l];
     switch (li.type) {
-      case ENUM_LyrType::Conv: {
-        if (lp.ctrdLst.GetDimCnt() != 3 || lp.asmtLst.GetDimCnt() != 4) {
-          SetError("layer %d: conv parameters have unexpected rank", l + 1);
+      case QCNN_CONV: {
+        if (!lp.ctrd || !lp.asmt || !lp.bias) {
+          SetError("layer %d: conv layer without product-quantized parameters", l + 1);
           rc = 1;
           break;
         }
-        const int S = lp.ctrdLst.GetDimLen(0), K = lp.ctrdLst.GetDimLen(1), d = lp.ctrdLst.GetDimLen(2);
-        if (lp.asmtLst.GetDimLen(0) != li.knlCnt || lp.asmtLst.GetDimLen(1) != li.knlSiz ||
-            lp.asmtLst.GetDimLen(2) != li.knlSiz || lp.asmtLst.GetDimLen(3) != S ||
-            lp.biasVec.GetEleCnt() != li.knlCnt) {
-          SetError("layer %d: conv parameter shapes do not match the layer table", l + 1);
-          rc = 1;
-          break;
-        }
-        rc = qcnn_conv_layer_create(ctx, C, H, W, li.knlCnt, li.knlSiz, li.padSiz, li.stride, li.grpCnt, S, K, d,
-                                    lp.ctrdLst.GetDataPtr(), lp.asmtLst.GetDataPtr(), lp.biasVec.GetDataPtr(), &nl.pq);
+        rc = qcnn_conv_layer_create(ctx, C, H, W, li.knlCnt, li.knlSiz, li.padSiz, li.stride, li.grpCnt, lp.S, lp.K, lp.d,
+                                    lp.ctrd, lp.asmt, lp.bias, &nl.pq);
         if (rc) break;
         H = nl.pq->Ho; W = nl.pq->Wo; C = li.knlCnt;
         break;
       }
-      case ENUM_LyrType::FCnt: {
-        if (lp.ctrdLst.GetDimCnt() != 3 || lp.asmtLst.GetDimCnt() != 2) {
-          SetError("layer %d: FC parameters have unexpected rank", l + 1);
+      case QCNN_FCNT: {
+        if (!lp.ctrd || !lp.asmt || !lp.bias) {
+          SetError("layer %d: FC layer without product-quantized parameters", l + 1);
           rc = 1;
           break;
         }
-        const int S = lp.ctrdLst.GetDimLen(0), K = lp.ctrdLst.GetDimLen(1), d = lp.ctrdLst.GetDimLen(2);
         const int Din = H * W * C;
-        if (lp.asmtLst.GetDimLen(0) != li.nodCnt || lp.asmtLst.GetDimLen(1) != S || lp.biasVec.GetEleCnt() != li.nodCnt) {
-          SetError("layer %d: FC parameter shapes do not match the layer table", l + 1);
-          rc = 1;
-          break;
-        }
-        rc = qcnn_fc_layer_create(ctx, Din, li.nodCnt, S, K, d, lp.ctrdLst.GetDataPtr(), lp.asmtLst.GetDataPtr(),
-                                  lp.biasVec.GetDataPtr(), &nl.pq);
+        rc = qcnn_fc_layer_create(ctx, Din, li.nodCnt, lp.S, lp.K, lp.d, lp.ctrd, lp.asmt, lp.bias, &nl.pq);
         if (rc) break;
         // first FC layer: the reference permutes its NHWC input to NCHW first (CaffeEva.cc:236-238)
         if (!seenFc && (H > 1 || W > 1)) rc = qcnn_fc_layer_set_src_nhwc(nl.pq, H, W, C);
@@ -146,7 +129,7 @@ static int BuildNet(qcnn_ctx* ctx, CaffePara& para, qcnn_net** out) {
         H = 1; W = 1; C = li.nodCnt;
         break;
       }
-      case ENUM_LyrType::Pool:
+      case QCNN_POOL:
         H = PoolOut(H, li.padSiz, li.knlSiz, li.stride);
         W = PoolOut(W, li.padSiz, li.knlSiz, li.stride);
         break;
@@ -175,7 +158,47 @@ static int BuildNet(qcnn_ctx* ctx, CaffePara& para, qcnn_net** out) {
   return 0;
 }
 
+// parameters loaded from files: shape checks against the layer table, then the common builder
+static int BuildFromCaffePara(qcnn_ctx* ctx, CaffePara& para, qcnn_net** out) {
+  std::vector<qcnn_layer_info> infos(para.layerCnt);
+  std::vector<qcnn_layer_para> paras(para.layerCnt);
+  for (int l = 0; l < para.layerCnt; l++) {
+    const LayerInfo& li = para.layerInfoLst[l];
+    qcnn_layer_info& o = infos[l];
+    o.type = static_cast<int>(li.type);
+    o.padSiz = li.padSiz; o.knlSiz = li.knlSiz; o.knlCnt = li.knlCnt; o.grpCnt = li.grpCnt; o.stride = li.stride;
+    o.nodCnt = li.nodCnt; o.lrnSiz = li.lrnSiz; o.lrnAlp = li.lrnAlp; o.lrnBet = li.lrnBet; o.lrnIni = li.lrnIni; o.drpRat = li.drpRat;
+    memset(&paras[l], 0, sizeof(qcnn_layer_para));
+    if (li.type != ENUM_LyrType::Conv && li.type != ENUM_LyrType::FCnt) continue;
+    const LayerPara& lp = para.layerParaLst[l];
+    const bool conv = li.type == ENUM_LyrType::Conv;
+    QCNN_CHECK(lp.ctrdLst.GetDimCnt() == 3 && lp.asmtLst.GetDimCnt() == (conv ? 4 : 2),
+               "layer %d: %s parameters have unexpected rank", l + 1, conv ? "conv" : "FC");
+    const int S = lp.ctrdLst.GetDimLen(0);
+    if (conv)
+      QCNN_CHECK(lp.asmtLst.GetDimLen(0) == li.knlCnt && lp.asmtLst.GetDimLen(1) == li.knlSiz && lp.asmtLst.GetDimLen(2) == li.knlSiz &&
+                 lp.asmtLst.GetDimLen(3) == S && lp.biasVec.GetEleCnt() == li.knlCnt,
+                 "layer %d: conv parameter shapes do not match the layer table", l + 1);
+    else
+      QCNN_CHECK(lp.asmtLst.GetDimLen(0) == li.nodCnt && lp.asmtLst.GetDimLen(1) == S && lp.biasVec.GetEleCnt() == li.nodCnt,
+                 "layer %d: FC parameter shapes do not match the layer table", l + 1);
+    paras[l].ctrd = lp.ctrdLst.GetDataPtr(); paras[l].asmt = lp.asmtLst.GetDataPtr(); paras[l].bias = lp.biasVec.GetDataPtr();
+    paras[l].S = S; paras[l].K = lp.ctrdLst.GetDimLen(1); paras[l].d = lp.ctrdLst.GetDimLen(2);
+  }
+  return BuildNet(ctx, para.layerCnt, infos.data(), paras.data(), para.imgChnIn, para.imgHeiIn, para.imgWidIn, out);
+}
+
 extern "C" {
+
+int qcnn_net_create_from_para(qcnn_ctx* ctx, int layer_cnt, const qcnn_layer_info* layers, const qcnn_layer_para* para,
+                              int img_chn, int img_hei, int img_wid, qcnn_net** out) {
+  QCNN_CHECK(ctx && layers && para && out && layer_cnt >= 1, "qcnn_net_create_from_para: bad argument");
+  *out = nullptr;
+  for (int l = 0; l < layer_cnt; l++)
+    QCNN_CHECK(layers[l].type >= 0 && layers[l].type <= QCNN_SMAX, "qcnn_net_create_from_para: layer %d has invalid type", l);
+  QCNN_CUDA(cudaSetDevice(ctx->device));
+  return BuildNet(ctx, layer_cnt, layers, para, img_chn, img_hei, img_wid, out);
+}
 
 int qcnn_net_create(qcnn_ctx* ctx, const char* model_name, const char* dir, const char* pfx, qcnn_net** out) {
   QCNN_CHECK(ctx && model_name && dir && pfx && out, "qcnn_net_create: NULL argument");
@@ -185,7 +208,7 @@ int qcnn_net_create(qcnn_ctx* ctx, const char* model_name, const char* dir, cons
   QCNN_CHECK(para.ConfigLayer_ByName(model_name), "qcnn_net_create: unrecognized caffe model name: %s", model_name);
   QCNN_CHECK(para.LoadLayerPara(true, ENUM_AsmtEnc::Compact), "qcnn_net_create: could not load parameters from %s/%s.*",
              dir, pfx);
-  return BuildNet(ctx, para, out);
+  return BuildFromCaffePara(ctx, para, out);
 }
 
 int qcnn_net_create_custom(qcnn_ctx* ctx, int layer_cnt, const qcnn_layer_info* layers, int img_chn, int img_hei,
@@ -208,7 +231,7 @@ int qcnn_net_create_custom(qcnn_ctx* ctx, int layer_cnt, const qcnn_layer_info* 
   }
   QCNN_CHECK(para.LoadLayerPara(true, ENUM_AsmtEnc::Compact),
              "qcnn_net_create_custom: could not load parameters from %s/%s.*", dir, pfx);
-  return BuildNet(ctx, para, out);
+  return BuildFromCaffePara(ctx, para, out);
 }
 
 void qcnn_net_destroy(qcnn_net* net) {

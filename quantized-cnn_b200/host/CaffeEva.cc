@@ -14,9 +14,11 @@ const int kEvalCntDefault = 100;  // the reference scores kDataCntInBatch * kBat
 }  // namespace
 
 CaffeEva::CaffeEva(void)
-    : enblAprx(true), device(0), evalCnt(kEvalCntDefault), evalBatch(256), ctx(nullptr), net(nullptr), msAllLayers(0.0) {}
+    : enblAprx(true), device(0), deviceCnt(1), evalCnt(kEvalCntDefault), evalBatch(256), ctx(nullptr), net(nullptr), multi(nullptr),
+      msAllLayers(0.0) {}
 
 CaffeEva::~CaffeEva(void) {
+  if (multi) qcnn_multi_destroy(multi);
   if (net) qcnn_net_destroy(net);
   if (ctx) qcnn_ctx_destroy(ctx);
 }
@@ -63,8 +65,42 @@ bool CaffeEva::LoadCaffePara(void) {
   if (!caffeParaObj.LoadLayerPara(enblAprx, ENUM_AsmtEnc::Compact)) return false;  // host copy, as the reference keeps
   if (!ctx && qcnn_ctx_create(device, &ctx) != 0) return Fail("qcnn_ctx_create");
   if (net) { qcnn_net_destroy(net); net = nullptr; }
-  if (qcnn_net_create(ctx, modelName.c_str(), dirPathMain.c_str(), fileNamePfx.c_str(), &net) != 0)
-    return Fail("qcnn_net_create");
+  // the parameters were read ONCE, above; the device network is built from these host matrices (the re-layout and
+  // upload PrepCtrdBuf / PrepAsmtBuf do on the CPU, reference src/CaffeEva.cc:534-623, happen inside the call)
+  std::vector<qcnn_layer_info> infos(caffeParaObj.layerCnt);
+  std::vector<qcnn_layer_para> paras(caffeParaObj.layerCnt);
+  for (int l = 0; l < caffeParaObj.layerCnt; l++) {
+    const LayerInfo& li = caffeParaObj.layerInfoLst[l];
+    qcnn_layer_info& o = infos[l];
+    o.type = static_cast<int>(li.type);
+    o.padSiz = li.padSiz; o.knlSiz = li.knlSiz; o.knlCnt = li.knlCnt; o.grpCnt = li.grpCnt; o.stride = li.stride;
+    o.nodCnt = li.nodCnt; o.lrnSiz = li.lrnSiz; o.lrnAlp = li.lrnAlp; o.lrnBet = li.lrnBet; o.lrnIni = li.lrnIni; o.drpRat = li.drpRat;
+    qcnn_layer_para& q = paras[l];
+    q.ctrd = nullptr; q.asmt = nullptr; q.bias = nullptr; q.S = q.K = q.d = 0;
+    if (li.type != ENUM_LyrType::Conv && li.type != ENUM_LyrType::FCnt) continue;
+    const LayerPara& lp = caffeParaObj.layerParaLst[l];
+    const bool conv = li.type == ENUM_LyrType::Conv;
+    const int S = lp.ctrdLst.GetDimLen(0);
+    const bool ok = lp.ctrdLst.GetDimCnt() == 3 && lp.asmtLst.GetDimCnt() == (conv ? 4 : 2) &&
+                    (conv ? (lp.asmtLst.GetDimLen(0) == li.knlCnt && lp.asmtLst.GetDimLen(1) == li.knlSiz &&
+                             lp.asmtLst.GetDimLen(2) == li.knlSiz && lp.asmtLst.GetDimLen(3) == S && lp.biasVec.GetEleCnt() == li.knlCnt)
+                          : (lp.asmtLst.GetDimLen(0) == li.nodCnt && lp.asmtLst.GetDimLen(1) == S && lp.biasVec.GetEleCnt() == li.nodCnt));
+    if (!ok) {
+      errorMsg = "layer " + std::to_string(l + 1) + ": parameter shapes do not match the layer table";
+      printf("[ERROR] %s\n", errorMsg.c_str());
+      return false;
+    }
+    q.ctrd = lp.ctrdLst.GetDataPtr(); q.asmt = lp.asmtLst.GetDataPtr(); q.bias = lp.biasVec.GetDataPtr();
+    q.S = S; q.K = lp.ctrdLst.GetDimLen(1); q.d = lp.ctrdLst.GetDimLen(2);
+  }
+  if (qcnn_net_create_from_para(ctx, caffeParaObj.layerCnt, infos.data(), paras.data(), caffeParaObj.imgChnIn,
+                                caffeParaObj.imgHeiIn, caffeParaObj.imgWidIn, &net) != 0)
+    return Fail("qcnn_net_create_from_para");
+  if (multi) { qcnn_multi_destroy(multi); multi = nullptr; }
+  if (deviceCnt > 1 &&
+      qcnn_multi_create_from_para(deviceCnt, nullptr, caffeParaObj.layerCnt, infos.data(), paras.data(), caffeParaObj.imgChnIn,
+                                  caffeParaObj.imgHeiIn, caffeParaObj.imgWidIn, &multi) != 0)
+    return Fail("qcnn_multi_create_from_para");
   qcnn_net_set_profiling(net, 1);
   msIndvLayerLst.assign(caffeParaObj.layerCnt, 0.0);
   return true;
@@ -86,6 +122,10 @@ void CaffeEva::ExecForwardPass(const Matrix<float>& imgDataIn, Matrix<float>* pP
   const int dataCnt = imgDataIn.GetDimLen(0);
   const int outLen = qcnn_net_out_len(net);
   pProbVecOut->Resize(dataCnt * outLen);
+  if (multi) {   // batch sharded over the GPUs of this process
+    if (qcnn_multi_forward_h(multi, imgDataIn.GetDataPtr(), dataCnt, pProbVecOut->GetDataPtr()) != 0) Fail("qcnn_multi_forward_h");
+    return;
+  }
   if (qcnn_net_forward_h(net, imgDataIn.GetDataPtr(), dataCnt, pProbVecOut->GetDataPtr(), nullptr) != 0) {
     Fail("qcnn_net_forward_h");
     return;
@@ -103,11 +143,18 @@ void CaffeEva::ExecForwardPass(void) {
   std::vector<float> prob(static_cast<size_t>(evalBatch) * outLen);
   for (int beg = 0; beg < dataCnt; beg += evalBatch) {
     const int cnt = std::min(evalBatch, dataCnt - beg);
-    if (qcnn_net_forward_h(net, dataLst.GetDataPtr() + beg * imgLen, cnt, prob.data(), nullptr) != 0) {
-      Fail("qcnn_net_forward_h");
-      return;
+    if (multi) {
+      if (qcnn_multi_forward_h(multi, dataLst.GetDataPtr() + beg * imgLen, cnt, prob.data()) != 0) {
+        Fail("qcnn_multi_forward_h");
+        return;
+      }
+    } else {
+      if (qcnn_net_forward_h(net, dataLst.GetDataPtr() + beg * imgLen, cnt, prob.data(), nullptr) != 0) {
+        Fail("qcnn_net_forward_h");
+        return;
+      }
+      AccumulateTimes();
     }
-    AccumulateTimes();
     CvtFeatMapToLablVec(beg, beg + cnt - 1, prob.data(), outLen);
   }
 }

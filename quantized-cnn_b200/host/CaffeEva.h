@@ -36,6 +36,9 @@ class CaffeEva {
 
   // extensions (not in the reference)
   void SetDevice(const int deviceInd) { device = deviceInd; }
+  // > 1: ExecForwardPass shards every batch over GPUs 0 .. n-1 of this process (qcnn_multi_*: replicas + NCCL all-gather
+  // of the probabilities); call before LoadCaffePara
+  void SetDeviceCount(const int deviceCntSrc) { deviceCnt = deviceCntSrc < 1 ? 1 : deviceCntSrc; }
   void SetEvalCount(const int imgCnt, const int batchSiz) { evalCnt = imgCnt; evalBatch = batchSiz; }
   const std::string& GetErrorMsg(void) const { return errorMsg; }
   const CaffePara& GetCaffePara(void) const { return caffeParaObj; }
@@ -55,6 +58,7 @@ class CaffeEva {
  private:
   bool enblAprx;
   int device;
+  int deviceCnt;
   int evalCnt, evalBatch;
   std::string modelName, dirPathMain, fileNamePfx, errorMsg;
   CaffePara caffeParaObj;
@@ -63,6 +67,7 @@ class CaffeEva {
   Matrix<uint16_t> lablVecPred;
   qcnn_ctx* ctx;
   qcnn_net* net;
+  qcnn_multi* multi;                 // deviceCnt > 1: the sharded executor (net stays for the per-layer members)
   double msAllLayers;                // accumulated device time of ExecForwardPass calls since the last DispElpsTime
   std::vector<double> msIndvLayerLst;
 

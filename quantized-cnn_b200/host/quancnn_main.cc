@@ -1,7 +1,7 @@
 // Command-line driver in the spirit of the reference's src/Main.cc + src/UnitTest.cc (which pick a mode by editing
 // the source): the mode and paths are arguments here.
 //   quancnn_b200 classify <mainDir> <clsNames> <imgLabels|-> <topk> <bmp>...      == UnitTest::UT_CaffeEvaWrapper
-//   quancnn_b200 layers   <mainDir>                                               per-layer CalcFeatMap_* smoke run
+//   quancnn_b200 layers   <mainDir> [deviceCnt]                                   per-layer CalcFeatMap_* run vs the fused pass
 // Output of `classify`: one line per image  "<file> gt=<name|-> time=<s> | idx:prob idx:prob ..."
 #include <cstdio>
 #include <cstdlib>
@@ -33,9 +33,10 @@ static int Classify(int argc, char** argv) {
 // Runs the network layer by layer through the per-layer CalcFeatMap_* members (host matrices in and out, exactly how
 // the reference's executor calls them) and compares the result with the fused whole-network path.
 static int Layers(int argc, char** argv) {
-  if (argc < 3) { fprintf(stderr, "usage: quancnn_b200 layers <mainDir>\n"); return 2; }
+  if (argc < 3) { fprintf(stderr, "usage: quancnn_b200 layers <mainDir> [deviceCnt]\n"); return 2; }
   CaffeEva eva;
   eva.Init(true);
+  if (argc >= 4) eva.SetDeviceCount(atoi(argv[3]));   // > 1: the fused pass is sharded over that many GPUs
   eva.SetModelName("AlexNet");
   eva.SetModelPath(std::string(argv[2]) + "/AlexNet/Bin.Files", "bvlc_alexnet_aCaF");
   if (!eva.LoadCaffePara()) return 1;

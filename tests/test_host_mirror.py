@@ -103,3 +103,18 @@ def test_per_layer_members_agree_with_fused_network():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("LAYERS")][0]
     assert "argmax0=533" in line            # SURVEY.md Appendix B synthetic KAT
+    # probabilities of the layer-by-layer run (host matrices between layers, un-fused kernels) vs the fused device pass
+    err = float(line.split("max|layerwise-fused|=")[1])
+    assert err <= 2e-5, line
+
+
+@pytest.mark.gpu
+@needs_data
+def test_host_executor_shards_over_all_gpus():
+    """CaffeEva::SetDeviceCount(n): ExecForwardPass through qcnn_multi_* (n = every GPU of the box, 1 included)."""
+    import torch
+    n = max(1, min(torch.cuda.device_count(), 8))
+    out = subprocess.run([os.path.join(PKG, "quancnn_b200"), "layers", DATA, str(n)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("LAYERS")][0]
+    assert "argmax0=533" in line

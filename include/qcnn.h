@@ -170,7 +170,21 @@ QCNN_API int qcnn_net_set_keep_maps(qcnn_net* net, int keep);
 QCNN_API int qcnn_net_forward(qcnn_net* net, const float* img, int N, float* prob, float* logits, void* stream);
 /* host-buffer forward == CaffeEva::ExecForwardPass(imgDataIn, pProbVecOut): H2D, forward, D2H, synchronises. */
 QCNN_API int qcnn_net_forward_h(qcnn_net* net, const float* img_h, int N, float* prob_h, float* logits_h);
-/* images per pipeline chunk of qcnn_net_forward_h (default 64): H2D of chunk c+1 overlaps compute of chunk c */
+/* same, with the k-fold arg-max of CaffeEvaWrapper::Proc (src/CaffeEvaWrapper.cc:188-206; topk_mode 0) or
+ * CaffeEva::CvtFeatMapToLablVec (src/CaffeEva.cc:1162-1190: the scan starts from FLT_MIN; topk_mode 1) done on the
+ * device: topk_idx_h [N][topk] int32 and topk_prob_h [N][topk] come back instead of (prob_h nullable) the whole rows */
+QCNN_API int qcnn_net_forward_topk_h(qcnn_net* net, const float* img_h, int N, int topk, int topk_mode, int* topk_idx_h,
+                                     float* topk_prob_h, float* prob_h);
+/* uint8 entry: images as interleaved pixels [N][H][W][C] (C = B, G, R for the shipped models), the crop-sized mean image
+ * [C][H][W] (NULL: none) subtracted on the device -- (float)pixel - mean, the element BmpImgIO::RmMeanImg produces
+ * (src/BmpImgIO.cc:203-224) -- before the first layer.  4x fewer bytes cross the host link than with fp32 tensors. */
+QCNN_API int qcnn_net_set_input_mean(qcnn_net* net, const float* mean_h);
+QCNN_API int qcnn_net_forward_u8(qcnn_net* net, const uint8_t* img, int N, float* prob, float* logits, void* stream);
+/* host pixels in, top-k (topk > 0) and / or probabilities (prob_h != NULL) out; synchronises */
+QCNN_API int qcnn_net_forward_u8_h(qcnn_net* net, const uint8_t* img_h, int N, int topk, int topk_mode, int* topk_idx_h,
+                                   float* topk_prob_h, float* prob_h);
+/* images per pipeline chunk of the host-buffer entry points (default 128; the first chunk of a call is a quarter of
+ * that): H2D of chunk c+1 overlaps the layers of chunk c */
 QCNN_API int qcnn_net_set_chunk(qcnn_net* net, int chunk);
 /* after a forward with keep_maps: device pointer + dims [N,H,W,C] of featMapLst[idx] */
 QCNN_API int qcnn_net_featmap(qcnn_net* net, int idx, const float** ptr, int* dims4);
@@ -184,6 +198,26 @@ QCNN_API int qcnn_net_layer_work(qcnn_net* net, int layer, int N, double* alg_by
 QCNN_API int qcnn_net_launch_count(const qcnn_net* net);
 /* PQ layer handle of layer `l` (NULL for non-PQ layers); owned by the net */
 QCNN_API qcnn_layer* qcnn_net_pq_layer(qcnn_net* net, int l);
+
+/* ---- image entry and result exit on the device -------------------------------------------
+ * k-fold arg-max of N rows of C values: first maximum wins, winner zeroed (mode: see qcnn_net_forward_topk_h);
+ * idx [N][k] int32, val [N][k], device */
+QCNN_API int qcnn_topk(qcnn_ctx* ctx, const float* prob, int N, int C, int k, int mode, int* idx, float* val, void* stream);
+/* src u8 [N][H][W][C] -> dst f32 [N][C][H][W] minus mean [C][H][W] (nullable), device */
+QCNN_API int qcnn_u8hwc_to_f32chw(qcnn_ctx* ctx, const uint8_t* src, const float* mean, float* dst, int N, int C, int H, int W,
+                                  void* stream);
+/* BmpImgIO on the device: == BmpImgIO::Init (src/BmpImgIO.cc:28-38).  resz_type 0 Strict / 1 Relaxed, mean_type 0 Full /
+ * 1 Crop (include/BmpImgIO.h:19-20); mean_h [3][mean_hei][mean_wid] in B, G, R plane order (imagenet_mean.single.bin) */
+typedef struct qcnn_preproc qcnn_preproc;
+QCNN_API int qcnn_preproc_create(qcnn_ctx* ctx, int resz_type, int mean_type, int hei_full, int wid_full, int hei_crop,
+                                 int wid_crop, const float* mean_h, int mean_hei, int mean_wid, qcnn_preproc** out);
+QCNN_API void qcnn_preproc_destroy(qcnn_preproc* p);
+/* == BmpImgIO::Load after the file decode -- ReszImg, RmMeanImg, CropImg (src/BmpImgIO.cc:105-224) -- for N decoded
+ * images in one launch, bit-identical to the CPU path: pix (device) holds the images' interleaved B, G, R bytes, top row
+ * first, image i of hei_h[i] x wid_h[i] pixels starting at byte off_h[i] (host arrays); dst [N][3][hei_crop][wid_crop]
+ * f32 NCHW (device), what ExecForwardPass takes */
+QCNN_API int qcnn_preproc_run(qcnn_preproc* p, const uint8_t* pix, const long long* off_h, const int* hei_h, const int* wid_h,
+                              int N, float* dst, void* stream);
 
 /* ---- multi-GPU: ONE process drives n_dev GPUs of a box -----------------------------------------
  * The batch is sharded by image (rank r owns rows [r*per, min(N, (r+1)*per)), per = ceil(N / n_dev)), the weights are

@@ -93,6 +93,10 @@ _SIGS = {
     "qcnn_net_set_keep_maps": (_i, [_vp, _i]),
     "qcnn_net_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "qcnn_net_forward_h": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "qcnn_net_forward_topk_h": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "qcnn_net_set_input_mean": (_i, [_vp, _vp]),
+    "qcnn_net_forward_u8": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "qcnn_net_forward_u8_h": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "qcnn_net_set_chunk": (_i, [_vp, _i]),
     "qcnn_net_featmap": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i)]),
     "qcnn_net_set_profiling": (_i, [_vp, _i]),
@@ -100,6 +104,11 @@ _SIGS = {
     "qcnn_net_layer_work": (_i, [_vp, _i, _i, _dp, _dp, _dp]),
     "qcnn_net_launch_count": (_i, [_vp]),
     "qcnn_net_pq_layer": (_vp, [_vp, _i]),
+    "qcnn_topk": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "qcnn_u8hwc_to_f32chw": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "qcnn_preproc_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, C.POINTER(_vp)]),
+    "qcnn_preproc_destroy": (None, [_vp]),
+    "qcnn_preproc_run": (_i, [_vp, _vp, C.POINTER(C.c_longlong), C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp]),
     "qcnn_multi_create": (_i, [_i, C.POINTER(_i), _cp, _cp, _cp, C.POINTER(_vp)]),
     "qcnn_multi_create_from_para": (_i, [_i, C.POINTER(_i), _i, C.POINTER(LayerInfo), _vp, _i, _i, _i, C.POINTER(_vp)]),
     "qcnn_multi_destroy": (None, [_vp]),
@@ -206,6 +215,15 @@ class Context(object):
         y = torch.empty_like(x)
         _check(lib.qcnn_softmax(self.h, _dptr(x), _dptr(y), x.shape[0], x.numel() // x.shape[0], _stream(stream)))
         return y
+
+    def topk(self, prob, k, mode=0, stream=None):
+        """k-fold arg-max (first maximum wins, winner zeroed) of every row; returns (idx int32 [N,k], val [N,k])."""
+        import torch
+        N, Cc = prob.shape
+        idx = torch.empty((N, k), dtype=torch.int32, device=prob.device)
+        val = torch.empty((N, k), dtype=torch.float32, device=prob.device)
+        _check(lib.qcnn_topk(self.h, _dptr(prob), N, Cc, k, mode, C.c_void_p(idx.data_ptr()), _dptr(val), _stream(stream)))
+        return idx, val
 
     def nchw_to_nhwc(self, x, stream=None):
         import torch
@@ -371,6 +389,51 @@ class Net(object):
         _check(lib.qcnn_net_forward_h(self.h, ptr(img_h), N, ptr(prob_h), ptr(logits_h) if logits_h is not None else None))
         return prob_h
 
+    def set_input_mean(self, mean_chw):
+        if mean_chw is None:
+            _check(lib.qcnn_net_set_input_mean(self.h, None))
+        else:
+            m = _np(mean_chw, np.float32)
+            _check(lib.qcnn_net_set_input_mean(self.h, m.ctypes.data_as(_vp)))
+
+    def forward_u8(self, img_u8, prob=None, logits=None, stream=None):
+        """img_u8: CUDA uint8 [N,H,W,C] interleaved pixels; returns prob [N,out_len] (device)."""
+        import torch
+        N = img_u8.shape[0]
+        if prob is None:
+            prob = torch.empty((N, self.out_len), dtype=torch.float32, device=img_u8.device)
+        assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+        _check(lib.qcnn_net_forward_u8(self.h, C.c_void_p(img_u8.data_ptr()), N, _dptr(prob),
+                                       _dptr(logits) if logits is not None else None, _stream(stream)))
+        return prob
+
+    @staticmethod
+    def _hptr(a):
+        if a is None:
+            return None
+        return C.c_void_p(a.data_ptr()) if hasattr(a, "data_ptr") else a.ctypes.data_as(_vp)
+
+    def forward_topk_host(self, img_h, k, mode=0, idx_h=None, val_h=None, prob_h=None):
+        """fp32 host images in, on-device top-k out: (idx int32 [N,k], prob [N,k])."""
+        N = img_h.shape[0]
+        idx_h = np.empty((N, k), np.int32) if idx_h is None else idx_h
+        val_h = np.empty((N, k), np.float32) if val_h is None else val_h
+        _check(lib.qcnn_net_forward_topk_h(self.h, self._hptr(img_h), N, k, mode, self._hptr(idx_h), self._hptr(val_h),
+                                           self._hptr(prob_h)))
+        return idx_h, val_h
+
+    def forward_u8_host(self, img_h, k=0, mode=0, idx_h=None, val_h=None, prob_h=None):
+        """uint8 host pixels [N,H,W,C] in; top-k (k > 0) and / or probabilities (prob_h) out."""
+        N = img_h.shape[0]
+        if k > 0:
+            idx_h = np.empty((N, k), np.int32) if idx_h is None else idx_h
+            val_h = np.empty((N, k), np.float32) if val_h is None else val_h
+        elif prob_h is None:
+            prob_h = np.empty((N, self.out_len), np.float32)
+        _check(lib.qcnn_net_forward_u8_h(self.h, self._hptr(img_h), N, k, mode, self._hptr(idx_h), self._hptr(val_h),
+                                         self._hptr(prob_h)))
+        return (idx_h, val_h) if k > 0 else prob_h
+
     def featmap(self, idx, N):
         """featMapLst[idx] of the last forward as a torch view [N,H,W,C] (None if fused away)."""
         import torch
@@ -401,6 +464,40 @@ class Net(object):
     def pq_layer(self, l):
         h = lib.qcnn_net_pq_layer(self.h, l)
         return _Layer(self.ctx, _vp(h), owned=False) if h else None
+
+
+class Preproc(object):
+    """BmpImgIO on the device (ReszImg, RmMeanImg, CropImg of decoded BMP pixels), qcnn_preproc_*."""
+
+    def __init__(self, ctx, mean_chw, hei_full=256, wid_full=256, hei_crop=227, wid_crop=227, resz_type=0, mean_type=0):
+        m = _np(mean_chw, np.float32)
+        assert m.ndim == 3 and m.shape[0] == 3
+        h = _vp()
+        _check(lib.qcnn_preproc_create(ctx.h, resz_type, mean_type, hei_full, wid_full, hei_crop, wid_crop,
+                                       m.ctypes.data_as(_vp), m.shape[1], m.shape[2], C.byref(h)))
+        self.h, self.ctx, self.crop = h, ctx, (hei_crop, wid_crop)
+
+    def close(self):
+        if self.h:
+            lib.qcnn_preproc_destroy(self.h)
+            self.h = None
+
+    def run(self, images, stream=None):
+        """images: list of uint8 numpy arrays [H,W,3] (B,G,R interleaved, top row first); returns CUDA f32 [N,3,hc,wc]."""
+        import torch
+        N = len(images)
+        offs, total = [], 0
+        for im in images:
+            offs.append(total)
+            total += im.size
+        flat = np.concatenate([np.ascontiguousarray(im, np.uint8).reshape(-1) for im in images])
+        pix = torch.from_numpy(flat).to("cuda:%d" % self.ctx.device)
+        out = torch.empty((N, 3) + self.crop, dtype=torch.float32, device=pix.device)
+        off = (C.c_longlong * N)(*offs)
+        hei = (_i * N)(*[im.shape[0] for im in images])
+        wid = (_i * N)(*[im.shape[1] for im in images])
+        _check(lib.qcnn_preproc_run(self.h, C.c_void_p(pix.data_ptr()), off, hei, wid, N, _dptr(out), _stream(stream)))
+        return out
 
 
 class MultiNet(object):

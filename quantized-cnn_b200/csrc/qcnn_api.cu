@@ -51,7 +51,7 @@ int qcnn_ctx_create(int device, qcnn_ctx** out) {
   QCNN_CUDA(cudaGetDeviceProperties(&prop, device));
   QCNN_CHECK(prop.major == 10, "qcnn_ctx_create: device %d is sm_%d%d; this build carries sm_100a code only", device,
              prop.major, prop.minor);
-  QCNN_CUDA(cudaSetDevice(device));
+  QCNN_ON_DEVICE(device);
   qcnn_ctx* ctx = new qcnn_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
@@ -69,27 +69,31 @@ int qcnn_ctx_sm_count(const qcnn_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int qcnn_dev_alloc(qcnn_ctx* ctx, size_t bytes, void** out) {
   QCNN_CHECK(ctx && out, "qcnn_dev_alloc: NULL argument");
-  QCNN_CUDA(cudaSetDevice(ctx->device));
+  QCNN_ON_DEVICE(ctx->device);
   QCNN_CUDA(cudaMalloc(out, bytes ? bytes : 1));
   return 0;
 }
 int qcnn_dev_free(qcnn_ctx* ctx, void* ptr) {
   QCNN_CHECK(ctx, "qcnn_dev_free: NULL ctx");
+  QCNN_ON_DEVICE(ctx->device);
   if (ptr) QCNN_CUDA(cudaFree(ptr));
   return 0;
 }
 int qcnn_copy_h2d(qcnn_ctx* ctx, void* dst, const void* src_h, size_t bytes, void* stream) {
   QCNN_CHECK(ctx && dst && src_h, "qcnn_copy_h2d: NULL argument");
+  QCNN_ON_DEVICE(ctx->device);
   QCNN_CUDA(cudaMemcpyAsync(dst, src_h, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 int qcnn_copy_d2h(qcnn_ctx* ctx, void* dst_h, const void* src, size_t bytes, void* stream) {
   QCNN_CHECK(ctx && dst_h && src, "qcnn_copy_d2h: NULL argument");
+  QCNN_ON_DEVICE(ctx->device);
   QCNN_CUDA(cudaMemcpyAsync(dst_h, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 int qcnn_stream_sync(qcnn_ctx* ctx, void* stream) {
   QCNN_CHECK(ctx, "qcnn_stream_sync: NULL ctx");
+  QCNN_ON_DEVICE(ctx->device);
   QCNN_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return 0;
 }
@@ -125,7 +129,7 @@ int qcnn_conv_layer_create(qcnn_ctx* ctx, int Cin, int Hin, int Win, int Cout, i
   QCNN_CHECK(K % 8 == 0, "qcnn_conv_layer_create: K=%d must be a multiple of 8 (LUT stage tiles 8 codewords)", K);
   const int taps = ksz * ksz;
   if (int rc = CheckPq("qcnn_conv_layer_create", S, K, d, asmt_h, static_cast<size_t>(Cout) * taps * S)) return rc;
-  QCNN_CUDA(cudaSetDevice(ctx->device));
+  QCNN_ON_DEVICE(ctx->device);
   qcnn_layer* L = NewLayer(ctx, QCNN_KIND_CONV);
   L->Cin = Cin; L->Hin = Hin; L->Win = Win; L->Cout = Cout; L->ksz = ksz; L->pad = pad; L->stride = stride;
   L->grp = grp; L->S = S; L->K = K; L->d = d;
@@ -173,7 +177,7 @@ int qcnn_fc_layer_create(qcnn_ctx* ctx, int Din, int Dout, int S, int K, int d, 
   if (int rc = CheckPq("qcnn_fc_layer_create", S, K, d, asmt_h, static_cast<size_t>(Dout) * S)) return rc;
   QCNN_CHECK(K == 16 || K == 32 || K == 64 || K == 128 || K == 256,
              "qcnn_fc_layer_create: unsupported codebook size K=%d (supported: 16, 32, 64, 128, 256)", K);
-  QCNN_CUDA(cudaSetDevice(ctx->device));
+  QCNN_ON_DEVICE(ctx->device);
   qcnn_layer* L = NewLayer(ctx, QCNN_KIND_FC);
   L->Din = Din; L->Dout = Dout; L->S = S; L->K = K; L->d = d;
   L->Ho = 1; L->Wo = 1; L->Cout = Dout;
@@ -206,6 +210,7 @@ int qcnn_fc_layer_create(qcnn_ctx* ctx, int Din, int Dout, int S, int K, int d, 
 
 int qcnn_fc_layer_set_src_nhwc(qcnn_layer* L, int H, int W, int C) {
   QCNN_CHECK(L && L->kind == QCNN_KIND_FC, "qcnn_fc_layer_set_src_nhwc: not an FC layer");
+  QCNN_ON_DEVICE(L->ctx->device);
   L->ctx->alloc_epoch++;   // captured graphs may hold the old offset table / kernel choice
   if (L->d_srcoff) { cudaFree(L->d_srcoff); L->d_srcoff = nullptr; }
   if (H == 0 && W == 0 && C == 0) { L->src_h = L->src_w = L->src_c = 0; return 0; }
@@ -271,6 +276,7 @@ int qcnn_layer_describe(qcnn_layer* L, int N, char* buf, size_t cap) {
 
 void qcnn_layer_destroy(qcnn_layer* L) {
   if (!L) return;
+  DeviceGuard guard(L->ctx->device);
   if (L->d_asmt) cudaFree(L->d_asmt);
   if (L->d_ctrd) cudaFree(L->d_ctrd);
   if (L->d_bias) cudaFree(L->d_bias);
@@ -330,6 +336,7 @@ int qcnn_layer_work(const qcnn_layer* L, int N, double* alg_bytes, double* looku
 
 int qcnn_layer_read_asmt_h(const qcnn_layer* L, uint8_t* out_h, size_t cap) {
   QCNN_CHECK(L && out_h, "qcnn_layer_read_asmt_h: NULL argument");
+  QCNN_ON_DEVICE(L->ctx->device);
   std::vector<uint8_t> dev(L->asmt_bytes);
   QCNN_CUDA(cudaMemcpy(dev.data(), L->d_asmt, dev.size(), cudaMemcpyDeviceToHost));
   if (L->kind == QCNN_KIND_CONV) {
@@ -353,19 +360,19 @@ int qcnn_layer_read_asmt_h(const qcnn_layer* L, uint8_t* out_h, size_t cap) {
 
 int qcnn_conv_aprx_forward(qcnn_layer* L, const float* src, int N, float* dst, int fuse_relu, void* stream) {
   QCNN_CHECK(L && src && dst, "qcnn_conv_aprx_forward: NULL argument");
-  QCNN_CUDA(cudaSetDevice(L->ctx->device));
+  QCNN_ON_DEVICE(L->ctx->device);
   return LaunchConv(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
 }
 
 int qcnn_fc_aprx_forward(qcnn_layer* L, const float* src, int N, float* dst, int fuse_relu, void* stream) {
   QCNN_CHECK(L && src && dst, "qcnn_fc_aprx_forward: NULL argument");
-  QCNN_CUDA(cudaSetDevice(L->ctx->device));
+  QCNN_ON_DEVICE(L->ctx->device);
   return LaunchFc(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
 }
 
 int qcnn_fc_aprx_forward_flat(qcnn_layer* L, const float* src, int N, float* dst, int fuse_relu, void* stream) {
   QCNN_CHECK(L && src && dst, "qcnn_fc_aprx_forward_flat: NULL argument");
-  QCNN_CUDA(cudaSetDevice(L->ctx->device));
+  QCNN_ON_DEVICE(L->ctx->device);
   int* saved = L->d_srcoff;
   L->d_srcoff = nullptr;
   const int rc = LaunchFc(L, src, N, dst, fuse_relu, static_cast<cudaStream_t>(stream));
@@ -378,7 +385,7 @@ int qcnn_fc_chain_forward(qcnn_layer* const* layers, const int* relu, int n, con
   QCNN_CHECK(layers && relu && src && dst && n >= 1 && n <= 4, "qcnn_fc_chain_forward: bad argument (1..4 layers)");
   for (int l = 0; l < n; l++) QCNN_CHECK(layers[l] && layers[l]->kind == QCNN_KIND_FC, "qcnn_fc_chain_forward: layer %d is not fully-connected", l);
   QCNN_CHECK(N >= 1 && N <= 4, "qcnn_fc_chain_forward: N must be in [1, 4] (got %d)", N);
-  QCNN_CUDA(cudaSetDevice(layers[0]->ctx->device));
+  QCNN_ON_DEVICE(layers[0]->ctx->device);
   bool handled = false;
   if (int rc = LaunchFcChain(layers[0]->ctx, layers, relu, n, src, N, dst, static_cast<cudaStream_t>(stream), stamps, &handled)) return rc;
   QCNN_CHECK(handled, "qcnn_fc_chain_forward: these layers are not supported by the fused kernel (shape, shared memory, "
@@ -388,34 +395,41 @@ int qcnn_fc_chain_forward(qcnn_layer* const* layers, const int* relu, int n, con
 
 int qcnn_relu(qcnn_ctx* ctx, const float* src, float* dst, size_t n, void* stream) {
   QCNN_CHECK(ctx && src && dst, "qcnn_relu: NULL argument");
+  QCNN_ON_DEVICE(ctx->device);
   return LaunchRelu(ctx, src, dst, n, static_cast<cudaStream_t>(stream));
 }
 int qcnn_lrn(qcnn_ctx* ctx, const float* src, float* dst, size_t pixels, int C, int size, float alpha, float beta,
              float k, void* stream) {
   QCNN_CHECK(ctx && src && dst, "qcnn_lrn: NULL argument");
+  QCNN_ON_DEVICE(ctx->device);
   return LaunchLrn(ctx, src, dst, pixels, C, size, alpha, beta, k, static_cast<cudaStream_t>(stream));
 }
 int qcnn_maxpool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int ksz, int pad, int stride,
                  void* stream) {
   QCNN_CHECK(ctx && src && dst, "qcnn_maxpool: NULL argument");
+  QCNN_ON_DEVICE(ctx->device);
   return LaunchMaxPool(ctx, src, dst, N, H, W, C, ksz, pad, stride, static_cast<cudaStream_t>(stream));
 }
 int qcnn_lrn_maxpool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, int size, float alpha,
                      float beta, float k, int ksz, int pad, int stride, void* stream) {
   QCNN_CHECK(ctx && src && dst, "qcnn_lrn_maxpool: NULL argument");
+  QCNN_ON_DEVICE(ctx->device);
   return LaunchLrnMaxPool(ctx, src, dst, N, H, W, C, size, alpha, beta, k, ksz, pad, stride,
                           static_cast<cudaStream_t>(stream));
 }
 int qcnn_softmax(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, void* stream) {
   QCNN_CHECK(ctx && src && dst, "qcnn_softmax: NULL argument");
+  QCNN_ON_DEVICE(ctx->device);
   return LaunchSoftmax(ctx, src, dst, N, C, static_cast<cudaStream_t>(stream));
 }
 int qcnn_nchw_to_nhwc(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, int H, int W, void* stream) {
   QCNN_CHECK(ctx && src && dst, "qcnn_nchw_to_nhwc: NULL argument");
+  QCNN_ON_DEVICE(ctx->device);
   return LaunchNchwToNhwc(ctx, src, dst, N, C, H, W, static_cast<cudaStream_t>(stream));
 }
 int qcnn_nhwc_to_nchw(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, void* stream) {
   QCNN_CHECK(ctx && src && dst, "qcnn_nhwc_to_nchw: NULL argument");
+  QCNN_ON_DEVICE(ctx->device);
   return LaunchNhwcToNchw(ctx, src, dst, N, H, W, C, static_cast<cudaStream_t>(stream));
 }
 

@@ -31,6 +31,27 @@ int CudaFail(cudaError_t e, const char* what, const char* file, int line);
     }                                    \
   } while (0)
 
+// Every entry point that needs a particular GPU makes it current for the duration of the call and puts the caller's
+// device back on return: the CUDA "current device" is process-visible state (PyTorch's default device IS the runtime's),
+// and a library that leaves it changed silently moves the caller's next allocation to another GPU.
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int device) : prev_(-1), err_(cudaSuccess) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+    if (prev_ != device) err_ = cudaSetDevice(device); else prev_ = -1;   // nothing to restore when already current
+  }
+  ~DeviceGuard() { if (prev_ >= 0) cudaSetDevice(prev_); }
+  cudaError_t error() const { return err_; }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+ private:
+  int prev_;
+  cudaError_t err_;
+};
+#define QCNN_ON_DEVICE(dev)                 \
+  ::qcnn::DeviceGuard device_guard__(dev);  \
+  QCNN_CUDA(device_guard__.error())
+
 inline int CeilDiv(int a, int b) { return (a + b - 1) / b; }
 inline int RoundUp(int a, int b) { return CeilDiv(a, b) * b; }
 
@@ -200,6 +221,10 @@ int LaunchLrnMaxPool(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, 
 int LaunchSoftmax(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, cudaStream_t st);
 int LaunchNchwToNhwc(qcnn_ctx* ctx, const float* src, float* dst, int N, int C, int H, int W, cudaStream_t st);
 int LaunchNhwcToNchw(qcnn_ctx* ctx, const float* src, float* dst, int N, int H, int W, int C, cudaStream_t st);
+
+// preproc.cu
+int LaunchU8ToF32(qcnn_ctx* ctx, const uint8_t* src, const float* mean, float* dst, int N, int C, int HW, cudaStream_t st);
+int LaunchTopK(qcnn_ctx* ctx, const float* prob, int N, int C, int k, int mode, int* idx, float* val, cudaStream_t st);
 
 inline int PoolOut(int in, int pad, int ksz, int stride) {
   // ceil((in + 2p - k) / s) + 1   (reference src/CaffeEva.cc:365-372)

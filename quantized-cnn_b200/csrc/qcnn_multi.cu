@@ -65,6 +65,13 @@ NcclApi* LoadNccl() {
 
 }  // namespace
 
+// puts the caller's current device back when a multi-GPU call returns
+struct RestoreDevice {
+  int prev;
+  RestoreDevice() : prev(-1) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~RestoreDevice() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct qcnn_multi {
   int R;
   std::vector<int> dev;
@@ -163,6 +170,7 @@ extern "C" {
 
 void qcnn_multi_destroy(qcnn_multi* m) {
   if (!m) return;
+  RestoreDevice restore;
   for (int r = 0; r < m->R; r++) {
     cudaSetDevice(m->dev[r]);
     if (m->stComp[r]) cudaStreamSynchronize(m->stComp[r]);
@@ -188,6 +196,7 @@ void qcnn_multi_destroy(qcnn_multi* m) {
 
 int qcnn_multi_create(int n_dev, const int* devices, const char* model_name, const char* dir, const char* pfx, qcnn_multi** out) {
   QCNN_CHECK(out && model_name && dir && pfx && n_dev >= 1 && n_dev <= 64, "qcnn_multi_create: bad argument");
+  RestoreDevice restore;
   *out = nullptr;
   NcclApi* api = LoadNccl();
   if (!api) return 3;
@@ -207,6 +216,7 @@ int qcnn_multi_create(int n_dev, const int* devices, const char* model_name, con
 int qcnn_multi_create_from_para(int n_dev, const int* devices, int layer_cnt, const qcnn_layer_info* layers,
                                 const qcnn_layer_para* para, int img_chn, int img_hei, int img_wid, qcnn_multi** out) {
   QCNN_CHECK(out && layers && para && n_dev >= 1 && n_dev <= 64, "qcnn_multi_create_from_para: bad argument");
+  RestoreDevice restore;
   *out = nullptr;
   NcclApi* api = LoadNccl();
   if (!api) return 3;
@@ -238,6 +248,7 @@ int qcnn_multi_nccl_version(const qcnn_multi* m) {
 // [N][out_len] probabilities on device r (a library-owned buffer, valid until the step after next).
 int qcnn_multi_forward(qcnn_multi* m, const float* const* img_dev, int N, const float** prob_all_dev) {
   QCNN_CHECK(m && img_dev && N >= 1, "qcnn_multi_forward: bad argument");
+  RestoreDevice restore;
   int per, lo, hi;
   ShardRange(N, m->R, 0, &per, &lo, &hi);
   if (int rc = EnsureMultiCapacity(m, per, false)) return rc;
@@ -275,6 +286,7 @@ int qcnn_multi_forward(qcnn_multi* m, const float* const* img_dev, int N, const 
 
 int qcnn_multi_sync(qcnn_multi* m) {
   QCNN_CHECK(m, "qcnn_multi_sync: NULL argument");
+  RestoreDevice restore;
   for (int r = 0; r < m->R; r++) {
     QCNN_CUDA(cudaSetDevice(m->dev[r]));
     QCNN_CUDA(cudaStreamSynchronize(m->stComp[r]));
@@ -288,6 +300,7 @@ int qcnn_multi_sync(qcnn_multi* m) {
 // gathered [N][out_len] probabilities comes back; synchronises.
 int qcnn_multi_forward_h(qcnn_multi* m, const float* img_h, int N, float* prob_h) {
   QCNN_CHECK(m && img_h && prob_h && N >= 1, "qcnn_multi_forward_h: bad argument");
+  RestoreDevice restore;
   int per, lo, hi;
   ShardRange(N, m->R, 0, &per, &lo, &hi);
   if (int rc = EnsureMultiCapacity(m, per, true)) return rc;

@@ -41,6 +41,15 @@ struct qcnn_net {
   // host-buffer forward: double-buffered input chunks + output staging
   float* d_in[2];
   size_t d_in_cap;
+  // uint8 entry points: crop-sized mean image, staging of the uint8 chunks, on-device top-k results
+  float* d_mean;            // [C][H][W] or NULL
+  uint8_t* d_in8[2];
+  size_t d_in8_cap;
+  float* d_f32;             // converted chunk (device-resident uint8 entry)
+  size_t d_f32_cap;
+  int* d_topi;
+  float* d_topv;
+  size_t d_top_cap;
   float* d_prob;
   float* d_logit;
   size_t d_out_cap;
@@ -88,9 +97,11 @@ static int BuildNet(qcnn_ctx* ctx, int layerCnt, const qcnn_layer_info* infos, c
   net->imgC = imgC; net->imgH = imgH; net->imgW = imgW;
   net->keep = 0; net->profiling = 0; net->capN = 0; net->lastLaunches = 0;
   net->d_in[0] = net->d_in[1] = nullptr; net->d_in_cap = 0;
+  net->d_mean = nullptr; net->d_in8[0] = net->d_in8[1] = nullptr; net->d_in8_cap = 0; net->d_f32 = nullptr; net->d_f32_cap = 0;
+  net->d_topi = nullptr; net->d_topv = nullptr; net->d_top_cap = 0;
   net->d_prob = net->d_logit = nullptr; net->d_out_cap = 0;
   net->stCopy = net->stComp = nullptr;
-  net->chunk = 64;
+  net->chunk = 128;
   int H = imgH, W = imgW, C = imgC;
   bool seenFc = false;
   int rc = 0;
@@ -196,7 +207,7 @@ int qcnn_net_create_from_para(qcnn_ctx* ctx, int layer_cnt, const qcnn_layer_inf
   *out = nullptr;
   for (int l = 0; l < layer_cnt; l++)
     QCNN_CHECK(layers[l].type >= 0 && layers[l].type <= QCNN_SMAX, "qcnn_net_create_from_para: layer %d has invalid type", l);
-  QCNN_CUDA(cudaSetDevice(ctx->device));
+  QCNN_ON_DEVICE(ctx->device);
   return BuildNet(ctx, layer_cnt, layers, para, img_chn, img_hei, img_wid, out);
 }
 
@@ -236,14 +247,19 @@ int qcnn_net_create_custom(qcnn_ctx* ctx, int layer_cnt, const qcnn_layer_info* 
 
 void qcnn_net_destroy(qcnn_net* net) {
   if (!net) return;
-  cudaSetDevice(net->ctx->device);
+  DeviceGuard guard(net->ctx->device);
   FreeMaps(net);
   for (NetLayer& L : net->layers) qcnn_layer_destroy(L.pq);
   for (size_t l = 0; l < net->evBeg.size(); l++) {
     cudaEventDestroy(net->evBeg[l]);
     cudaEventDestroy(net->evEnd[l]);
   }
+  if (net->d_mean) cudaFree(net->d_mean);
+  if (net->d_f32) cudaFree(net->d_f32);
+  if (net->d_topi) cudaFree(net->d_topi);
+  if (net->d_topv) cudaFree(net->d_topv);
   for (int i = 0; i < 2; i++) {
+    if (net->d_in8[i]) cudaFree(net->d_in8[i]);
     if (net->d_in[i]) cudaFree(net->d_in[i]);
     if (net->stCopy) { cudaEventDestroy(net->evH2D[i]); cudaEventDestroy(net->evDone[i]); }
   }
@@ -292,7 +308,7 @@ constexpr int kGraphMaxN = 8;
 int qcnn_net_forward(qcnn_net* net, const float* img, int N, float* prob, float* logits, void* stream) {
   QCNN_CHECK(net && img && prob, "qcnn_net_forward: NULL argument");
   QCNN_CHECK(N >= 1, "qcnn_net_forward: N must be >= 1");
-  QCNN_CUDA(cudaSetDevice(net->ctx->device));   // one process may drive several GPUs (qcnn_multi_*)
+  QCNN_ON_DEVICE(net->ctx->device);   // one process may drive several GPUs (qcnn_multi_*)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static const bool graphsOn = !(getenv("QCNN_GRAPH") && getenv("QCNN_GRAPH")[0] == '0');
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -495,10 +511,13 @@ static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, flo
   return 0;
 }
 
-int qcnn_net_forward_h(qcnn_net* net, const float* img_h, int N, float* prob_h, float* logits_h) {
-  QCNN_CHECK(net && img_h && prob_h, "qcnn_net_forward_h: NULL argument");
-  QCNN_CHECK(N >= 1, "qcnn_net_forward_h: N must be >= 1");
-  QCNN_CUDA(cudaSetDevice(net->ctx->device));
+// Host-buffer forward pass: a pipeline of chunks on two streams -- H2D of chunk c+1 (copy stream) overlaps the layers of
+// chunk c (compute stream).  Images arrive as fp32 NCHW (ExecForwardPass's own input) or as uint8 HWC pixels that are
+// converted (and mean-subtracted) on the device: 4x fewer bytes over the host link.  With topk > 0 the k-fold arg-max runs
+// on the device and only [N][k] (index, probability) pairs come back; prob_h / logits_h are optional then.
+static int ForwardHost(qcnn_net* net, const float* img_h, const uint8_t* img8_h, int N, float* prob_h, float* logits_h, int topk,
+                       int topk_mode, int* topi_h, float* topv_h) {
+  QCNN_ON_DEVICE(net->ctx->device);
   if (!net->stCopy) {
     QCNN_CUDA(cudaStreamCreateWithFlags(&net->stCopy, cudaStreamNonBlocking));
     QCNN_CUDA(cudaStreamCreateWithFlags(&net->stComp, cudaStreamNonBlocking));
@@ -517,6 +536,15 @@ int qcnn_net_forward_h(qcnn_net* net, const float* img_h, int N, float* prob_h, 
       QCNN_CUDA(cudaMalloc(&net->d_in[i], sizeof(float) * chunk * imgLen));
     }
     net->d_in_cap = chunk;
+    net->ctx->alloc_epoch++;
+  }
+  if (img8_h && static_cast<size_t>(chunk) > net->d_in8_cap) {
+    for (int i = 0; i < 2; i++) {
+      if (net->d_in8[i]) QCNN_CUDA(cudaFree(net->d_in8[i]));
+      net->d_in8[i] = nullptr;
+      QCNN_CUDA(cudaMalloc(&net->d_in8[i], chunk * imgLen));
+    }
+    net->d_in8_cap = chunk;
   }
   if (static_cast<size_t>(N) > net->d_out_cap) {
     if (net->d_prob) QCNN_CUDA(cudaFree(net->d_prob));
@@ -525,30 +553,102 @@ int qcnn_net_forward_h(qcnn_net* net, const float* img_h, int N, float* prob_h, 
     QCNN_CUDA(cudaMalloc(&net->d_prob, sizeof(float) * N * outLen));
     QCNN_CUDA(cudaMalloc(&net->d_logit, sizeof(float) * N * outLen));
     net->d_out_cap = N;
+    net->ctx->alloc_epoch++;
   }
-  // chunk pipeline: H2D of chunk c+1 (copy stream) overlaps the forward pass of chunk c (compute stream)
+  if (topk > 0 && static_cast<size_t>(N) * topk > net->d_top_cap) {
+    if (net->d_topi) QCNN_CUDA(cudaFree(net->d_topi));
+    if (net->d_topv) QCNN_CUDA(cudaFree(net->d_topv));
+    net->d_topi = nullptr; net->d_topv = nullptr;
+    QCNN_CUDA(cudaMalloc(&net->d_topi, sizeof(int) * N * topk));
+    QCNN_CUDA(cudaMalloc(&net->d_topv, sizeof(float) * N * topk));
+    net->d_top_cap = static_cast<size_t>(N) * topk;
+  }
   unsigned long long launches = 0;
   int ci = 0;
-  for (int n0 = 0; n0 < N; n0 += chunk, ci++) {
-    const int cn = std::min(chunk, N - n0);
+  // the first chunk is a quarter of the others: its host-to-device copy is the only one nothing overlaps
+  const int first = (N > chunk) ? std::max(1, chunk / 4) : chunk;
+  for (int n0 = 0; n0 < N; ci++) {
+    const int cn = std::min(ci == 0 ? first : chunk, N - n0);
     const int b = ci & 1;
     if (ci >= 2) QCNN_CUDA(cudaStreamWaitEvent(net->stCopy, net->evDone[b], 0));
-    QCNN_CUDA(cudaMemcpyAsync(net->d_in[b], img_h + n0 * imgLen, sizeof(float) * cn * imgLen, cudaMemcpyHostToDevice,
-                              net->stCopy));
+    if (img8_h)
+      QCNN_CUDA(cudaMemcpyAsync(net->d_in8[b], img8_h + n0 * imgLen, cn * imgLen, cudaMemcpyHostToDevice, net->stCopy));
+    else
+      QCNN_CUDA(cudaMemcpyAsync(net->d_in[b], img_h + n0 * imgLen, sizeof(float) * cn * imgLen, cudaMemcpyHostToDevice, net->stCopy));
     QCNN_CUDA(cudaEventRecord(net->evH2D[b], net->stCopy));
     QCNN_CUDA(cudaStreamWaitEvent(net->stComp, net->evH2D[b], 0));
+    if (img8_h) {
+      if (int rc = LaunchU8ToF32(net->ctx, net->d_in8[b], net->d_mean, net->d_in[b], cn, net->imgC, net->imgH * net->imgW, net->stComp)) return rc;
+      launches++;
+    }
     if (int rc = qcnn_net_forward(net, net->d_in[b], cn, net->d_prob + static_cast<size_t>(n0) * outLen,
                                   logits_h ? net->d_logit + static_cast<size_t>(n0) * outLen : nullptr, net->stComp))
       return rc;
     launches += net->lastLaunches;
     QCNN_CUDA(cudaEventRecord(net->evDone[b], net->stComp));
+    n0 += cn;
   }
-  QCNN_CUDA(cudaMemcpyAsync(prob_h, net->d_prob, sizeof(float) * N * outLen, cudaMemcpyDeviceToHost, net->stComp));
+  if (topk > 0) {
+    if (int rc = LaunchTopK(net->ctx, net->d_prob, N, outLen, topk, topk_mode, net->d_topi, net->d_topv, net->stComp)) return rc;
+    launches++;
+    QCNN_CUDA(cudaMemcpyAsync(topi_h, net->d_topi, sizeof(int) * N * topk, cudaMemcpyDeviceToHost, net->stComp));
+    QCNN_CUDA(cudaMemcpyAsync(topv_h, net->d_topv, sizeof(float) * N * topk, cudaMemcpyDeviceToHost, net->stComp));
+  }
+  if (prob_h) QCNN_CUDA(cudaMemcpyAsync(prob_h, net->d_prob, sizeof(float) * N * outLen, cudaMemcpyDeviceToHost, net->stComp));
   if (logits_h)
     QCNN_CUDA(cudaMemcpyAsync(logits_h, net->d_logit, sizeof(float) * N * outLen, cudaMemcpyDeviceToHost, net->stComp));
   QCNN_CUDA(cudaStreamSynchronize(net->stComp));
   net->lastLaunches = launches;
   return 0;
+}
+
+int qcnn_net_forward_h(qcnn_net* net, const float* img_h, int N, float* prob_h, float* logits_h) {
+  QCNN_CHECK(net && img_h && prob_h, "qcnn_net_forward_h: NULL argument");
+  QCNN_CHECK(N >= 1, "qcnn_net_forward_h: N must be >= 1");
+  return ForwardHost(net, img_h, nullptr, N, prob_h, logits_h, 0, 0, nullptr, nullptr);
+}
+
+int qcnn_net_forward_topk_h(qcnn_net* net, const float* img_h, int N, int topk, int topk_mode, int* topk_idx_h, float* topk_prob_h,
+                            float* prob_h) {
+  QCNN_CHECK(net && img_h && topk_idx_h && topk_prob_h, "qcnn_net_forward_topk_h: NULL argument");
+  QCNN_CHECK(N >= 1 && topk >= 1 && topk <= qcnn_net_out_len(net), "qcnn_net_forward_topk_h: bad N / topk");
+  return ForwardHost(net, img_h, nullptr, N, prob_h, nullptr, topk, topk_mode, topk_idx_h, topk_prob_h);
+}
+
+int qcnn_net_set_input_mean(qcnn_net* net, const float* mean_h) {
+  QCNN_CHECK(net, "qcnn_net_set_input_mean: NULL net");
+  QCNN_ON_DEVICE(net->ctx->device);
+  if (net->d_mean) { QCNN_CUDA(cudaFree(net->d_mean)); net->d_mean = nullptr; }
+  if (!mean_h) return 0;
+  const size_t bytes = sizeof(float) * net->imgC * net->imgH * net->imgW;
+  QCNN_CUDA(cudaMalloc(&net->d_mean, bytes));
+  QCNN_CUDA(cudaMemcpy(net->d_mean, mean_h, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int qcnn_net_forward_u8(qcnn_net* net, const uint8_t* img, int N, float* prob, float* logits, void* stream) {
+  QCNN_CHECK(net && img && prob && N >= 1, "qcnn_net_forward_u8: bad argument");
+  QCNN_ON_DEVICE(net->ctx->device);
+  const size_t imgLen = static_cast<size_t>(net->imgC) * net->imgH * net->imgW;
+  if (static_cast<size_t>(N) > net->d_f32_cap) {
+    if (net->d_f32) QCNN_CUDA(cudaFree(net->d_f32));
+    net->d_f32 = nullptr; net->d_f32_cap = 0;
+    QCNN_CUDA(cudaMalloc(&net->d_f32, sizeof(float) * N * imgLen));
+    net->d_f32_cap = N;
+    net->ctx->alloc_epoch++;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = LaunchU8ToF32(net->ctx, img, net->d_mean, net->d_f32, N, net->imgC, net->imgH * net->imgW, st)) return rc;
+  return qcnn_net_forward(net, net->d_f32, N, prob, logits, st);
+}
+
+int qcnn_net_forward_u8_h(qcnn_net* net, const uint8_t* img_h, int N, int topk, int topk_mode, int* topk_idx_h, float* topk_prob_h,
+                          float* prob_h) {
+  QCNN_CHECK(net && img_h && N >= 1, "qcnn_net_forward_u8_h: bad argument");
+  QCNN_CHECK(topk >= 0 && topk <= qcnn_net_out_len(net), "qcnn_net_forward_u8_h: bad topk");
+  QCNN_CHECK(topk == 0 || (topk_idx_h && topk_prob_h), "qcnn_net_forward_u8_h: topk > 0 needs the index and probability buffers");
+  QCNN_CHECK(topk > 0 || prob_h, "qcnn_net_forward_u8_h: nothing to return (topk == 0 and prob_h == NULL)");
+  return ForwardHost(net, nullptr, img_h, N, prob_h, nullptr, topk, topk_mode, topk_idx_h, topk_prob_h);
 }
 
 int qcnn_net_set_chunk(qcnn_net* net, int chunk) {
@@ -573,6 +673,7 @@ int qcnn_net_layer_time_ms(qcnn_net* net, int layer, float* ms) {
   QCNN_CHECK(layer >= 0 && layer < static_cast<int>(net->layers.size()), "qcnn_net_layer_time_ms: bad layer index");
   *ms = 0.0f;
   if (!net->evUsed[layer]) return 0;
+  QCNN_ON_DEVICE(net->ctx->device);
   QCNN_CUDA(cudaEventSynchronize(net->evEnd[layer]));
   QCNN_CUDA(cudaEventElapsedTime(ms, net->evBeg[layer], net->evEnd[layer]));
   return 0;

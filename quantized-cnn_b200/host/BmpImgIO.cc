@@ -38,9 +38,8 @@ bool BmpImgIO::Load(const std::string& filePath, Matrix<float>* pImgDataFnal) {
   return true;
 }
 
-// 24-bpp uncompressed BMP -> [1][3][H][W] in B, G, R plane order (reference src/BmpImgIO.cc:73-103 stores
-// B at channel 0, G at 1, R at 2; row 0 is the top of the picture)
-bool BmpImgIO::LoadBmpImg(const std::string& filePath, Matrix<float>* pImgData) {
+// 24-bpp uncompressed BMP -> interleaved B, G, R bytes (the file's own channel order), row 0 = top of the picture
+bool BmpImgIO::DecodeBmp(const std::string& filePath, std::vector<unsigned char>* pPixels, int* pHei, int* pWid) {
   FILE* f = fopen(filePath.c_str(), "rb");
   if (f == nullptr) {
     printf("[ERROR] cannot open the BMP image at %s\n", filePath.c_str());
@@ -61,7 +60,7 @@ bool BmpImgIO::LoadBmpImg(const std::string& filePath, Matrix<float>* pImgData) 
   const int hei = bottomUp ? heiRaw : -heiRaw;
   const size_t rowBytes = (static_cast<size_t>(wid) * 3 + 3) & ~static_cast<size_t>(3);
   std::vector<uint8_t> row(rowBytes);
-  pImgData->Create(1, kImgChn, hei, wid);
+  pPixels->resize(static_cast<size_t>(hei) * wid * 3);
   fseek(f, dataOff, SEEK_SET);
   for (int r = 0; r < hei; r++) {
     if (fread(row.data(), 1, rowBytes, f) != rowBytes) {
@@ -70,10 +69,24 @@ bool BmpImgIO::LoadBmpImg(const std::string& filePath, Matrix<float>* pImgData) 
       return false;
     }
     const int y = bottomUp ? hei - 1 - r : r;
-    for (int x = 0; x < wid; x++)
-      for (int c = 0; c < kImgChn; c++) pImgData->SetEleAt(row[3 * x + c], 0, c, y, x);  // file order is B, G, R
+    std::copy(row.begin(), row.begin() + static_cast<size_t>(wid) * 3, pPixels->begin() + static_cast<size_t>(y) * wid * 3);
   }
   fclose(f);
+  *pHei = hei;
+  *pWid = wid;
+  return true;
+}
+
+// 24-bpp uncompressed BMP -> [1][3][H][W] in B, G, R plane order (reference src/BmpImgIO.cc:73-103 stores
+// B at channel 0, G at 1, R at 2; row 0 is the top of the picture)
+bool BmpImgIO::LoadBmpImg(const std::string& filePath, Matrix<float>* pImgData) {
+  std::vector<unsigned char> pix;
+  int hei = 0, wid = 0;
+  if (!DecodeBmp(filePath, &pix, &hei, &wid)) return false;
+  pImgData->Create(1, kImgChn, hei, wid);
+  for (int y = 0; y < hei; y++)
+    for (int x = 0; x < wid; x++)
+      for (int c = 0; c < kImgChn; c++) pImgData->SetEleAt(pix[(static_cast<size_t>(y) * wid + x) * 3 + c], 0, c, y, x);
   return true;
 }
 

@@ -6,6 +6,7 @@
 #define QCNN_HOST_BMPIMGIO_H_
 
 #include <string>
+#include <vector>
 
 #include "Matrix.h"
 
@@ -26,6 +27,12 @@ class BmpImgIO {
  public:
   bool Init(const BmpImgIOPara& bmpImgIOPara);
   bool Load(const std::string& filePath, Matrix<float>* pImgDataFnal);
+
+  // extensions (not in the reference): the file decode alone -- interleaved B, G, R bytes, top row first -- for callers
+  // that run ReszImg / RmMeanImg / CropImg on the GPU (qcnn_preproc_*), and read access to the recipe
+  static bool DecodeBmp(const std::string& filePath, std::vector<unsigned char>* pPixels, int* pHei, int* pWid);
+  const BmpImgIOPara& GetPara(void) const { return para_; }
+  const Matrix<float>& GetMeanImg(void) const { return imgDataMean; }
 
  private:
   BmpImgIOPara para_;

@@ -14,10 +14,11 @@ const int kEvalCntDefault = 100;  // the reference scores kDataCntInBatch * kBat
 }  // namespace
 
 CaffeEva::CaffeEva(void)
-    : enblAprx(true), device(0), deviceCnt(1), evalCnt(kEvalCntDefault), evalBatch(256), ctx(nullptr), net(nullptr), multi(nullptr),
+    : enblAprx(true), device(0), deviceCnt(1), evalCnt(kEvalCntDefault), evalBatch(256), ctx(nullptr), net(nullptr), preproc(nullptr), multi(nullptr),
       msAllLayers(0.0) {}
 
 CaffeEva::~CaffeEva(void) {
+  if (preproc) qcnn_preproc_destroy(preproc);
   if (multi) qcnn_multi_destroy(multi);
   if (net) qcnn_net_destroy(net);
   if (ctx) qcnn_ctx_destroy(ctx);
@@ -104,6 +105,45 @@ bool CaffeEva::LoadCaffePara(void) {
   qcnn_net_set_profiling(net, 1);
   msIndvLayerLst.assign(caffeParaObj.layerCnt, 0.0);
   return true;
+}
+
+bool CaffeEva::SetPreproc(const int reszType, const int meanType, const int heiFull, const int widFull, const int heiCrop,
+                          const int widCrop, const Matrix<float>& meanImg) {
+  if (!ctx && qcnn_ctx_create(device, &ctx) != 0) return Fail("qcnn_ctx_create");
+  if (preproc) { qcnn_preproc_destroy(preproc); preproc = nullptr; }
+  if (qcnn_preproc_create(ctx, reszType, meanType, heiFull, widFull, heiCrop, widCrop, meanImg.GetDataPtr(), meanImg.GetDimLen(1),
+                          meanImg.GetDimLen(2), &preproc) != 0)
+    return Fail("qcnn_preproc_create");
+  return true;
+}
+
+bool CaffeEva::ClassifyPixels(const unsigned char* pixels, const int* hei, const int* wid, const int imgCnt, const int topk,
+                              std::vector<int>* pClsIdxLst, std::vector<float>* pClsProbLst) {
+  if (!net || !preproc) { errorMsg = "ClassifyPixels: LoadCaffePara() and SetPreproc() must have succeeded"; return false; }
+  pClsIdxLst->clear();
+  pClsProbLst->clear();
+  if (imgCnt < 1 || topk < 1) return true;
+  std::vector<long long> off(imgCnt);
+  size_t total = 0;
+  for (int i = 0; i < imgCnt; i++) { off[i] = static_cast<long long>(total); total += static_cast<size_t>(hei[i]) * wid[i] * 3; }
+  const int outLen = qcnn_net_out_len(net);
+  const size_t imgLen = static_cast<size_t>(caffeParaObj.imgChnIn) * caffeParaObj.imgHeiIn * caffeParaObj.imgWidIn;
+  void *dPix = nullptr, *dImg = nullptr, *dProb = nullptr, *dIdx = nullptr, *dVal = nullptr;
+  bool ok = qcnn_dev_alloc(ctx, total, &dPix) == 0 && qcnn_dev_alloc(ctx, sizeof(float) * imgCnt * imgLen, &dImg) == 0 &&
+            qcnn_dev_alloc(ctx, sizeof(float) * imgCnt * outLen, &dProb) == 0 &&
+            qcnn_dev_alloc(ctx, sizeof(int) * imgCnt * topk, &dIdx) == 0 && qcnn_dev_alloc(ctx, sizeof(float) * imgCnt * topk, &dVal) == 0;
+  pClsIdxLst->assign(static_cast<size_t>(imgCnt) * topk, 0);
+  pClsProbLst->assign(static_cast<size_t>(imgCnt) * topk, 0.0f);
+  ok = ok && qcnn_copy_h2d(ctx, dPix, pixels, total, nullptr) == 0 &&
+       qcnn_preproc_run(preproc, static_cast<const uint8_t*>(dPix), off.data(), hei, wid, imgCnt, static_cast<float*>(dImg), nullptr) == 0 &&
+       qcnn_net_forward(net, static_cast<const float*>(dImg), imgCnt, static_cast<float*>(dProb), nullptr, nullptr) == 0 &&
+       qcnn_topk(ctx, static_cast<const float*>(dProb), imgCnt, outLen, topk, 0, static_cast<int*>(dIdx), static_cast<float*>(dVal), nullptr) == 0 &&
+       qcnn_copy_d2h(ctx, pClsIdxLst->data(), dIdx, sizeof(int) * imgCnt * topk, nullptr) == 0 &&
+       qcnn_copy_d2h(ctx, pClsProbLst->data(), dVal, sizeof(float) * imgCnt * topk, nullptr) == 0 && qcnn_stream_sync(ctx, nullptr) == 0;
+  if (!ok) Fail("ClassifyPixels");
+  else AccumulateTimes();
+  qcnn_dev_free(ctx, dPix); qcnn_dev_free(ctx, dImg); qcnn_dev_free(ctx, dProb); qcnn_dev_free(ctx, dIdx); qcnn_dev_free(ctx, dVal);
+  return ok;
 }
 
 void CaffeEva::AccumulateTimes(void) {

@@ -40,6 +40,13 @@ class CaffeEva {
   // of the probabilities); call before LoadCaffePara
   void SetDeviceCount(const int deviceCntSrc) { deviceCnt = deviceCntSrc < 1 ? 1 : deviceCntSrc; }
   void SetEvalCount(const int imgCnt, const int batchSiz) { evalCnt = imgCnt; evalBatch = batchSiz; }
+  // Decoded pictures in, top-k out, everything between on the GPU: BmpImgIO's ReszImg / RmMeanImg / CropImg
+  // (qcnn_preproc_run), the forward pass, and the k-fold arg-max of CaffeEvaWrapper::Proc (qcnn_topk).  `pixels` holds
+  // imgCnt images back to back (interleaved B, G, R bytes, top row first; image i is hei[i] x wid[i]).
+  bool SetPreproc(const int reszType, const int meanType, const int heiFull, const int widFull, const int heiCrop,
+                  const int widCrop, const Matrix<float>& meanImg);
+  bool ClassifyPixels(const unsigned char* pixels, const int* hei, const int* wid, const int imgCnt, const int topk,
+                      std::vector<int>* pClsIdxLst, std::vector<float>* pClsProbLst);
   const std::string& GetErrorMsg(void) const { return errorMsg; }
   const CaffePara& GetCaffePara(void) const { return caffeParaObj; }
   const Matrix<uint16_t>& GetPredLabels(void) const { return lablVecPred; }
@@ -67,6 +74,7 @@ class CaffeEva {
   Matrix<uint16_t> lablVecPred;
   qcnn_ctx* ctx;
   qcnn_net* net;
+  qcnn_preproc* preproc;             // GPU BmpImgIO (SetPreproc)
   qcnn_multi* multi;                 // deviceCnt > 1: the sharded executor (net stays for the per-layer members)
   double msAllLayers;                // accumulated device time of ExecForwardPass calls since the last DispElpsTime
   std::vector<double> msIndvLayerLst;

@@ -56,18 +56,31 @@ bool CaffeEvaWrapper::SetModel(const ENUM_CaffeModel& caffeModelSrc, const ENUM_
     errorMsg = "[CaffeEvaWrapper::SetModel] could not load model files";
     return false;
   }
+  // the recipe above, on the device: Proc ships the decoded pixels and gets the top-k back
+  if (!caffeEvaObj.SetPreproc(r.resz == ENUM_ReszType::Strict ? 0 : 1, r.mean == ENUM_MeanType::Full ? 0 : 1, p.imgHeiFull,
+                              p.imgWidFull, p.imgHeiCrop, p.imgWidCrop, bmpImgIOObj.GetMeanImg())) {
+    errorMsg = "[CaffeEvaWrapper::SetModel] could not set up the device preprocessing: " + caffeEvaObj.GetErrorMsg();
+    return false;
+  }
   return true;
 }
 
 // reference src/CaffeEvaWrapper.cc:153-209
 bool CaffeEvaWrapper::Proc(const std::string& filePathProcImg, CaffeEvaRslt* pCaffeEvaRslt) {
-  Matrix<float> imgData;
-  if (!bmpImgIOObj.Load(filePathProcImg, &imgData)) {
+  // BMP decode on the host; resize, mean subtraction, crop (BmpImgIO::Load, :40-71), the forward pass and the top-k by
+  // repeated arg-max (first maximum wins, winner zeroed, :188-206) on the device
+  std::vector<unsigned char> pixels;
+  int hei = 0, wid = 0;
+  if (!BmpImgIO::DecodeBmp(filePathProcImg, &pixels, &hei, &wid)) {
     errorMsg = "[CaffeEvaWrapper::Proc] could open the BMP file";
     return false;
   }
-  Matrix<float> probVec;
-  caffeEvaObj.ExecForwardPass(imgData, &probVec);
+  std::vector<int> topIdx;
+  std::vector<float> topProb;
+  if (!caffeEvaObj.ClassifyPixels(pixels.data(), &hei, &wid, 1, pCaffeEvaRslt->clsCntPred, &topIdx, &topProb)) {
+    errorMsg = "[CaffeEvaWrapper::Proc] " + caffeEvaObj.GetErrorMsg();
+    return false;
+  }
   pCaffeEvaRslt->timeTotal = caffeEvaObj.DispElpsTime();
 
   const std::string fileName = ExtrFileName(filePathProcImg);
@@ -79,20 +92,14 @@ bool CaffeEvaWrapper::Proc(const std::string& filePathProcImg, CaffeEvaRslt* pCa
       break;
     }
   }
-  // top-k by repeated arg-max: first maximum wins, winner zeroed (reference :188-206)
-  const int clsCnt = probVec.GetEleCnt();
-  float* p = probVec.GetDataPtr();
   pCaffeEvaRslt->clsIdxLst.clear();
   pCaffeEvaRslt->clsProbLst.clear();
   pCaffeEvaRslt->clsNameLst.clear();
-  for (int rank = 0; rank < pCaffeEvaRslt->clsCntPred && clsCnt > 0; rank++) {
-    int best = 0;
-    for (int c = 1; c < clsCnt; c++)
-      if (p[best] < p[c]) best = c;
+  for (size_t rank = 0; rank < topIdx.size(); rank++) {
+    const int best = topIdx[rank];
     pCaffeEvaRslt->clsIdxLst.push_back(best);
-    pCaffeEvaRslt->clsProbLst.push_back(p[best]);
+    pCaffeEvaRslt->clsProbLst.push_back(topProb[rank]);
     pCaffeEvaRslt->clsNameLst.push_back(best < static_cast<int>(clsNameLst.size()) ? clsNameLst[best] : std::string());
-    p[best] = 0.0f;
   }
   return true;
 }

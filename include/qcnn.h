@@ -183,6 +183,13 @@ QCNN_API int qcnn_net_forward_u8(qcnn_net* net, const uint8_t* img, int N, float
 /* host pixels in, top-k (topk > 0) and / or probabilities (prob_h != NULL) out; synchronises */
 QCNN_API int qcnn_net_forward_u8_h(qcnn_net* net, const uint8_t* img_h, int N, int topk, int topk_mode, int* topk_idx_h,
                                    float* topk_prob_h, float* prob_h);
+/* asynchronous form: queues copy-in, conversion, forward pass, top-k and copy-out, then returns a ticket (0 or 1); the
+ * host buffers (pinned, or the copies are not asynchronous) belong to the step until qcnn_net_wait(ticket).  Two tickets
+ * may be outstanding -- the pixels of step i+1 travel while step i computes -- and a third submit first waits for the
+ * ticket two steps back.  Do not mix with the synchronous host entry points while tickets are outstanding. */
+QCNN_API int qcnn_net_submit_u8_h(qcnn_net* net, const uint8_t* img_h, int N, int topk, int topk_mode, int* topk_idx_h,
+                                  float* topk_prob_h, float* prob_h, int* ticket);
+QCNN_API int qcnn_net_wait(qcnn_net* net, int ticket);
 /* images per pipeline chunk of the host-buffer entry points (default 128; the first chunk of a call is a quarter of
  * that): H2D of chunk c+1 overlaps the layers of chunk c */
 QCNN_API int qcnn_net_set_chunk(qcnn_net* net, int chunk);

@@ -97,6 +97,8 @@ _SIGS = {
     "qcnn_net_set_input_mean": (_i, [_vp, _vp]),
     "qcnn_net_forward_u8": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "qcnn_net_forward_u8_h": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "qcnn_net_submit_u8_h": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_i)]),
+    "qcnn_net_wait": (_i, [_vp, _i]),
     "qcnn_net_set_chunk": (_i, [_vp, _i]),
     "qcnn_net_featmap": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i)]),
     "qcnn_net_set_profiling": (_i, [_vp, _i]),
@@ -433,6 +435,16 @@ class Net(object):
         _check(lib.qcnn_net_forward_u8_h(self.h, self._hptr(img_h), N, k, mode, self._hptr(idx_h), self._hptr(val_h),
                                          self._hptr(prob_h)))
         return (idx_h, val_h) if k > 0 else prob_h
+
+    def submit_u8_host(self, img_h, k=0, mode=0, idx_h=None, val_h=None, prob_h=None):
+        """Asynchronous uint8 step (pinned buffers); returns a ticket for wait()."""
+        t = _i()
+        _check(lib.qcnn_net_submit_u8_h(self.h, self._hptr(img_h), img_h.shape[0], k, mode, self._hptr(idx_h), self._hptr(val_h),
+                                        self._hptr(prob_h), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        _check(lib.qcnn_net_wait(self.h, ticket))
 
     def featmap(self, idx, N):
         """featMapLst[idx] of the last forward as a torch view [N,H,W,C] (None if fused away)."""

@@ -1293,6 +1293,16 @@ int PlanConv(qcnn_layer* L, int N) {
   L->cands->clear();
   // layer parameter "force_kernel" / QCNN_FORCE_KERNEL=<0 s1 | 1 roll | 2 s1_tc | 3 roll_tc | 4 direct | 6 pq_gemm_tc>
   // restricts the choice (tests pin the kernel they check; fails when that kernel has no tiling for the layer)
+  // Within the LUT + gather family the kernels come in two numerical classes -- fp32 LUT / decode (s1, roll, direct) and
+  // 3xTF32 tensor-core LUT stage (s1_tc, roll_tc; ~5e-6 apart) -- and on-device timing must not pick between classes
+  // either: the class of the cost model's favourite is kept, timing chooses among its tilings only.
+  if (!cands.empty() && cands[0].second.kernel != 6 && !L->opt_force_kernel && getenv("QCNN_FORCE_KERNEL") == nullptr) {
+    auto cls = [](int k) { return (k == 2 || k == 3) ? 1 : 0; };
+    const int want = cls(cands[0].second.kernel);
+    std::vector<std::pair<double, ConvPlan>> kept;
+    for (const auto& c : cands) if (c.second.kernel != 6 && cls(c.second.kernel) == want) kept.push_back(c);
+    cands.swap(kept);
+  }
   if (L->opt_gemm_nt) {   // layer parameter "gemm_nt": only pq_gemm_tc tilings with that many positions per CTA
     std::vector<std::pair<double, ConvPlan>> kept;
     for (const auto& c : cands) if (c.second.kernel != 6 || c.second.g.NT == L->opt_gemm_nt) kept.push_back(c);

@@ -50,6 +50,12 @@ struct qcnn_net {
   int* d_topi;
   float* d_topv;
   size_t d_top_cap;
+  // asynchronous host-buffer steps (qcnn_net_submit_u8_h): two input slots so that the copy of step i+1 overlaps step i
+  uint8_t* d_sub8[2];
+  size_t d_sub8_cap;
+  cudaEvent_t evSubIn[2], evSubRead[2], evSubDone[2];
+  int subInit;
+  unsigned long long subCount;
   float* d_prob;
   float* d_logit;
   size_t d_out_cap;
@@ -99,6 +105,7 @@ static int BuildNet(qcnn_ctx* ctx, int layerCnt, const qcnn_layer_info* infos, c
   net->d_in[0] = net->d_in[1] = nullptr; net->d_in_cap = 0;
   net->d_mean = nullptr; net->d_in8[0] = net->d_in8[1] = nullptr; net->d_in8_cap = 0; net->d_f32 = nullptr; net->d_f32_cap = 0;
   net->d_topi = nullptr; net->d_topv = nullptr; net->d_top_cap = 0;
+  net->d_sub8[0] = net->d_sub8[1] = nullptr; net->d_sub8_cap = 0; net->subInit = 0; net->subCount = 0;
   net->d_prob = net->d_logit = nullptr; net->d_out_cap = 0;
   net->stCopy = net->stComp = nullptr;
   net->chunk = 128;
@@ -259,6 +266,8 @@ void qcnn_net_destroy(qcnn_net* net) {
   if (net->d_topi) cudaFree(net->d_topi);
   if (net->d_topv) cudaFree(net->d_topv);
   for (int i = 0; i < 2; i++) {
+    if (net->d_sub8[i]) cudaFree(net->d_sub8[i]);
+    if (net->subInit) { cudaEventDestroy(net->evSubIn[i]); cudaEventDestroy(net->evSubRead[i]); cudaEventDestroy(net->evSubDone[i]); }
     if (net->d_in8[i]) cudaFree(net->d_in8[i]);
     if (net->d_in[i]) cudaFree(net->d_in[i]);
     if (net->stCopy) { cudaEventDestroy(net->evH2D[i]); cudaEventDestroy(net->evDone[i]); }
@@ -649,6 +658,102 @@ int qcnn_net_forward_u8_h(qcnn_net* net, const uint8_t* img_h, int N, int topk, 
   QCNN_CHECK(topk == 0 || (topk_idx_h && topk_prob_h), "qcnn_net_forward_u8_h: topk > 0 needs the index and probability buffers");
   QCNN_CHECK(topk > 0 || prob_h, "qcnn_net_forward_u8_h: nothing to return (topk == 0 and prob_h == NULL)");
   return ForwardHost(net, nullptr, img_h, N, prob_h, nullptr, topk, topk_mode, topk_idx_h, topk_prob_h);
+}
+
+// Asynchronous host-buffer step: queues H2D (copy stream) -> uint8 conversion, forward pass, top-k (compute stream) ->
+// D2H of the results, and returns a ticket.  Two tickets may be outstanding: the pixels of step i+1 travel while step i
+// computes, so a caller that keeps two steps in flight is bound by max(copy, compute) instead of their sum.
+int qcnn_net_submit_u8_h(qcnn_net* net, const uint8_t* img_h, int N, int topk, int topk_mode, int* topk_idx_h, float* topk_prob_h,
+                         float* prob_h, int* ticket) {
+  QCNN_CHECK(net && img_h && ticket && N >= 1, "qcnn_net_submit_u8_h: bad argument");
+  QCNN_CHECK(topk >= 0 && topk <= qcnn_net_out_len(net), "qcnn_net_submit_u8_h: bad topk");
+  QCNN_CHECK(topk == 0 || (topk_idx_h && topk_prob_h), "qcnn_net_submit_u8_h: topk > 0 needs the index and probability buffers");
+  QCNN_CHECK(topk > 0 || prob_h, "qcnn_net_submit_u8_h: nothing to return (topk == 0 and prob_h == NULL)");
+  QCNN_ON_DEVICE(net->ctx->device);
+  if (!net->stCopy) {
+    QCNN_CUDA(cudaStreamCreateWithFlags(&net->stCopy, cudaStreamNonBlocking));
+    QCNN_CUDA(cudaStreamCreateWithFlags(&net->stComp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      QCNN_CUDA(cudaEventCreateWithFlags(&net->evH2D[i], cudaEventDisableTiming));
+      QCNN_CUDA(cudaEventCreateWithFlags(&net->evDone[i], cudaEventDisableTiming));
+    }
+  }
+  if (!net->subInit) {
+    for (int i = 0; i < 2; i++) {
+      QCNN_CUDA(cudaEventCreateWithFlags(&net->evSubIn[i], cudaEventDisableTiming));
+      QCNN_CUDA(cudaEventCreateWithFlags(&net->evSubRead[i], cudaEventDisableTiming));
+      QCNN_CUDA(cudaEventCreateWithFlags(&net->evSubDone[i], cudaEventDisableTiming));
+    }
+    net->subInit = 1;
+  }
+  const size_t imgLen = static_cast<size_t>(net->imgC) * net->imgH * net->imgW;
+  const int outLen = qcnn_net_out_len(net);
+  const int s = static_cast<int>(net->subCount & 1);
+  if (net->subCount >= 2) QCNN_CUDA(cudaEventSynchronize(net->evSubDone[s]));   // the ticket two steps back must be over
+  // (re)allocations only while nothing is in flight that uses the buffers
+  if (static_cast<size_t>(N) > net->d_sub8_cap || static_cast<size_t>(N) > net->d_f32_cap || static_cast<size_t>(N) > net->d_out_cap ||
+      (topk > 0 && static_cast<size_t>(N) * topk > net->d_top_cap)) {
+    QCNN_CUDA(cudaStreamSynchronize(net->stCopy));
+    QCNN_CUDA(cudaStreamSynchronize(net->stComp));
+    if (static_cast<size_t>(N) > net->d_sub8_cap) {
+      for (int i = 0; i < 2; i++) {
+        if (net->d_sub8[i]) QCNN_CUDA(cudaFree(net->d_sub8[i]));
+        net->d_sub8[i] = nullptr;
+        QCNN_CUDA(cudaMalloc(&net->d_sub8[i], N * imgLen));
+      }
+      net->d_sub8_cap = N;
+    }
+    if (static_cast<size_t>(N) > net->d_f32_cap) {
+      if (net->d_f32) QCNN_CUDA(cudaFree(net->d_f32));
+      net->d_f32 = nullptr; net->d_f32_cap = 0;
+      QCNN_CUDA(cudaMalloc(&net->d_f32, sizeof(float) * N * imgLen));
+      net->d_f32_cap = N;
+      net->ctx->alloc_epoch++;
+    }
+    if (static_cast<size_t>(N) > net->d_out_cap) {
+      if (net->d_prob) QCNN_CUDA(cudaFree(net->d_prob));
+      if (net->d_logit) QCNN_CUDA(cudaFree(net->d_logit));
+      net->d_prob = net->d_logit = nullptr;
+      QCNN_CUDA(cudaMalloc(&net->d_prob, sizeof(float) * N * outLen));
+      QCNN_CUDA(cudaMalloc(&net->d_logit, sizeof(float) * N * outLen));
+      net->d_out_cap = N;
+      net->ctx->alloc_epoch++;
+    }
+    if (topk > 0 && static_cast<size_t>(N) * topk > net->d_top_cap) {
+      if (net->d_topi) QCNN_CUDA(cudaFree(net->d_topi));
+      if (net->d_topv) QCNN_CUDA(cudaFree(net->d_topv));
+      net->d_topi = nullptr; net->d_topv = nullptr;
+      QCNN_CUDA(cudaMalloc(&net->d_topi, sizeof(int) * N * topk));
+      QCNN_CUDA(cudaMalloc(&net->d_topv, sizeof(float) * N * topk));
+      net->d_top_cap = static_cast<size_t>(N) * topk;
+    }
+  }
+  // copy stream: the slot's pixels were last read by the conversion two steps back
+  if (net->subCount >= 2) QCNN_CUDA(cudaStreamWaitEvent(net->stCopy, net->evSubRead[s], 0));
+  QCNN_CUDA(cudaMemcpyAsync(net->d_sub8[s], img_h, N * imgLen, cudaMemcpyHostToDevice, net->stCopy));
+  QCNN_CUDA(cudaEventRecord(net->evSubIn[s], net->stCopy));
+  // compute stream: conversion, layers, top-k, results home
+  QCNN_CUDA(cudaStreamWaitEvent(net->stComp, net->evSubIn[s], 0));
+  if (int rc = LaunchU8ToF32(net->ctx, net->d_sub8[s], net->d_mean, net->d_f32, N, net->imgC, net->imgH * net->imgW, net->stComp)) return rc;
+  QCNN_CUDA(cudaEventRecord(net->evSubRead[s], net->stComp));
+  if (int rc = qcnn_net_forward(net, net->d_f32, N, net->d_prob, nullptr, net->stComp)) return rc;
+  if (topk > 0) {
+    if (int rc = LaunchTopK(net->ctx, net->d_prob, N, outLen, topk, topk_mode, net->d_topi, net->d_topv, net->stComp)) return rc;
+    QCNN_CUDA(cudaMemcpyAsync(topk_idx_h, net->d_topi, sizeof(int) * N * topk, cudaMemcpyDeviceToHost, net->stComp));
+    QCNN_CUDA(cudaMemcpyAsync(topk_prob_h, net->d_topv, sizeof(float) * N * topk, cudaMemcpyDeviceToHost, net->stComp));
+  }
+  if (prob_h) QCNN_CUDA(cudaMemcpyAsync(prob_h, net->d_prob, sizeof(float) * N * outLen, cudaMemcpyDeviceToHost, net->stComp));
+  QCNN_CUDA(cudaEventRecord(net->evSubDone[s], net->stComp));
+  *ticket = s;
+  net->subCount++;
+  return 0;
+}
+
+int qcnn_net_wait(qcnn_net* net, int ticket) {
+  QCNN_CHECK(net && (ticket == 0 || ticket == 1) && net->subInit, "qcnn_net_wait: bad ticket");
+  QCNN_ON_DEVICE(net->ctx->device);
+  QCNN_CUDA(cudaEventSynchronize(net->evSubDone[ticket]));
+  return 0;
 }
 
 int qcnn_net_set_chunk(qcnn_net* net, int chunk) {

@@ -98,7 +98,7 @@ def test_alexnet_synthetic_weights_all_feature_maps(po, qcnn, ctx, synth_dir, mo
     #     (chunks of 2 + 1 images run with their own tilings / kernel families, hence the mode's tolerance)
     net.set_chunk(2)
     ph = net.forward_host(img)
-    HT = 5e-6 if mode == "strict" else PT
+    HT = PT
     assert np.abs(ph - prob_f).max() <= HT
     pin = torch.from_numpy(img).pin_memory()
     out = torch.empty((N, 1000), dtype=torch.float32).pin_memory()

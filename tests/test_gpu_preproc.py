@@ -117,14 +117,14 @@ def test_topk_on_device(po, qcnn, ctx):
     rng = np.random.RandomState(4)
     p = rng.rand(37, 1000).astype(np.float32)
     p[3, 10] = p[3, 700] = 2.0            # tie for the maximum: the lower index wins, then the other one
-    p[5] = 0.0                            # all equal: indices 0, 1, 2, ... in turn (each winner is zeroed = stays equal)
+    p[5] = 0.0                            # all equal: index 0 every time (the zeroed winner is still a first maximum)
     p[6, :] = -1.0                        # nothing above zero: after the first winner is zeroed IT wins again
     idx, val = ctx.topk(torch.from_numpy(p).cuda(), 5)
     idx, val = idx.cpu().numpy(), val.cpu().numpy()
     for n in range(p.shape[0]):
         ri, rv = po.topk(p[n], 5)
         assert np.array_equal(idx[n], ri) and np.array_equal(val[n], rv), n
-    assert list(idx[3][:2]) == [10, 700] and list(idx[5]) == [0, 1, 2, 3, 4]
+    assert list(idx[3][:2]) == [10, 700] and list(idx[5]) == [0, 0, 0, 0, 0]
     # mode 1 = CaffeEva::CvtFeatMapToLablVec: the scan starts from (FLT_MIN, index 0)
     idx1, _ = ctx.topk(torch.from_numpy(p).cuda(), 5, mode=1)
     idx1 = idx1.cpu().numpy()
@@ -156,6 +156,25 @@ def test_uint8_entry_points_equal_the_fp32_entry(po, qcnn, ctx, tmp_path):
         ri, rv = po.topk(ph[n], 5)
         assert np.array_equal(idx[n], ri) and np.array_equal(val[n], rv)
         assert np.array_equal(idx2[n], ri) and np.array_equal(val2[n], rv)
+    # asynchronous form, two steps in flight (the second slot's pixels travel while the first step computes)
+    pin = [torch.from_numpy(pix).pin_memory(), torch.from_numpy(pix[::-1].copy()).pin_memory()]
+    wants = [want, net.forward_u8(pin[1].cuda()).cpu().numpy()]
+    oi = [torch.empty((N, 5), dtype=torch.int32).pin_memory() for _ in range(2)]
+    ov = [torch.empty((N, 5), dtype=torch.float32).pin_memory() for _ in range(2)]
+    op = [torch.empty((N, 1000), dtype=torch.float32).pin_memory() for _ in range(2)]
+    tickets = []
+    for step in range(5):
+        b = step & 1
+        if step >= 2:
+            net.wait(tickets[step - 2])
+            assert np.array_equal(op[b].numpy(), wants[b])
+        tickets.append(net.submit_u8_host(pin[b], k=5, idx_h=oi[b], val_h=ov[b], prob_h=op[b]))
+    net.wait(tickets[-2])
+    net.wait(tickets[-1])
+    assert np.array_equal(op[0].numpy(), wants[0]) and np.array_equal(op[1].numpy(), wants[1])
+    for n in range(N):
+        ri, rv = po.topk(want[n], 5)
+        assert np.array_equal(oi[0].numpy()[n], ri) and np.array_equal(ov[0].numpy()[n], rv)
     net.set_input_mean(None)
     assert np.array_equal(net.forward_u8(torch.from_numpy(pix).cuda()).cpu().numpy(),
                           net.forward(torch.from_numpy(np.ascontiguousarray(np.transpose(pix, (0, 3, 1, 2))).astype(np.float32)).cuda()).cpu().numpy())

@@ -24,6 +24,7 @@ void SetError(const char* fmt, ...) {
 
 int CudaFail(cudaError_t e, const char* what, const char* file, int line) {
   SetError("CUDA error %d (%s) at %s:%d: %s", static_cast<int>(e), cudaGetErrorString(e), file, line, what);
+  cudaGetLastError();   // reported: do not leave it behind for the next, unrelated, launch check to find
   return 2;
 }
 

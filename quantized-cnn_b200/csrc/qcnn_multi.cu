@@ -172,11 +172,13 @@ void qcnn_multi_destroy(qcnn_multi* m) {
   if (!m) return;
   RestoreDevice restore;
   for (int r = 0; r < m->R; r++) {
+    if (!m->ctx[r]) continue;          // creation failed before this rank (e.g. a device that does not exist)
     cudaSetDevice(m->dev[r]);
     if (m->stComp[r]) cudaStreamSynchronize(m->stComp[r]);
     if (m->stGath[r]) cudaStreamSynchronize(m->stGath[r]);
   }
   for (int r = 0; r < m->R; r++) {
+    if (!m->ctx[r]) continue;
     cudaSetDevice(m->dev[r]);
     if (m->comm[r] && m->nccl) m->nccl->CommDestroy(m->comm[r]);
     for (int b = 0; b < 2; b++) {
@@ -191,6 +193,7 @@ void qcnn_multi_destroy(qcnn_multi* m) {
     if (m->net[r]) qcnn_net_destroy(m->net[r]);
     if (m->ctx[r]) qcnn_ctx_destroy(m->ctx[r]);
   }
+  cudaGetLastError();
   delete m;
 }
 

@@ -74,8 +74,6 @@ struct qcnn_net {
   std::vector<GraphEntry> graphs;
 };
 
-static size_t MapElems(const NetLayer& L) { return static_cast<size_t>(L.Hout) * L.Wout * L.Cout; }
-
 static void FreeMaps(qcnn_net* net) {
   for (float*& p : net->maps) {
     if (p) cudaFree(p);
@@ -83,17 +81,33 @@ static void FreeMaps(qcnn_net* net) {
   }
   net->capN = 0;
 }
+static size_t MapElems(const NetLayer& L) { return static_cast<size_t>(L.Hout) * L.Wout * L.Cout; }
 
+// Feature-map buffers are allocated on first use at the current batch capacity: the fused production path touches
+// about half of featMapLst (ReLU / LRN / dropout outputs are fused away), so the other half is never allocated unless
+// keep_maps asks for it.  A larger batch frees everything and raises the capacity.
 static int EnsureCapacity(qcnn_net* net, int N) {
+  if (net->maps.empty()) net->maps.assign(net->layers.size() + 1, nullptr);
   if (N <= net->capN) return 0;
   FreeMaps(net);
   net->ctx->alloc_epoch++;
-  const size_t L = net->layers.size();
-  net->maps.assign(L + 1, nullptr);
-  QCNN_CUDA(cudaMalloc(&net->maps[0], sizeof(float) * N * net->imgC * net->imgH * net->imgW));
-  for (size_t l = 0; l < L; l++) QCNN_CUDA(cudaMalloc(&net->maps[l + 1], sizeof(float) * N * MapElems(net->layers[l])));
   net->capN = N;
   return 0;
+}
+
+static float* MapBuf(qcnn_net* net, int idx, cudaStream_t st) {
+  if (net->maps[idx]) return net->maps[idx];
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st) cudaStreamIsCapturing(st, &cap);
+  if (cap != cudaStreamCaptureStatusNone) { SetError("internal: feature map %d is not allocated inside a stream capture", idx); return nullptr; }
+  const size_t elems = idx == 0 ? static_cast<size_t>(net->imgC) * net->imgH * net->imgW : MapElems(net->layers[idx - 1]);
+  if (cudaMalloc(&net->maps[idx], sizeof(float) * net->capN * elems) != cudaSuccess) {
+    CudaFail(cudaGetLastError(), "cudaMalloc(feature map)", __FILE__, __LINE__);
+    net->maps[idx] = nullptr;
+    return nullptr;
+  }
+  net->ctx->alloc_epoch++;
+  return net->maps[idx];
 }
 
 static int BuildNet(qcnn_ctx* ctx, int layerCnt, const qcnn_layer_info* infos, const qcnn_layer_para* paras, int imgC, int imgH,
@@ -396,10 +410,14 @@ static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, flo
   } else {
     if (firstReadsNchw) {
       cur = img;  // conv still reads the NCHW input; also materialise the NHWC map for inspection
-      if (int rc = LaunchNchwToNhwc(ctx, img, net->maps[0], N, net->imgC, net->imgH, net->imgW, st)) return rc;
+      float* m0 = MapBuf(net, 0, st);
+      if (!m0) return 2;
+      if (int rc = LaunchNchwToNhwc(ctx, img, m0, N, net->imgC, net->imgH, net->imgW, st)) return rc;
     } else {
-      if (int rc = LaunchNchwToNhwc(ctx, img, net->maps[0], N, net->imgC, net->imgH, net->imgW, st)) return rc;
-      cur = net->maps[0];
+      float* m0 = MapBuf(net, 0, st);
+      if (!m0) return 2;
+      if (int rc = LaunchNchwToNhwc(ctx, img, m0, N, net->imgC, net->imgH, net->imgW, st)) return rc;
+      cur = m0;
     }
     net->mapPtr[0] = net->maps[0];
   }
@@ -433,7 +451,8 @@ static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, flo
           }
           if (n >= 1 && FcChainEligible(ctx, chain, crelu, n, N)) {
             bool handled = false;
-            float* dst = net->maps[outIdx];
+            float* dst = MapBuf(net, outIdx, st);
+        if (!dst) return 2;
             rc = LaunchFcChain(ctx, chain, crelu, n, cur, N, dst, st, nullptr, &handled);
             if (rc) break;
             if (handled) {
@@ -446,7 +465,8 @@ static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, flo
         }
         const bool fuse = !net->keep && l + 1 < L && net->layers[l + 1].info.type == QCNN_RELU;
         const int outIdx = fuse ? l + 2 : l + 1;
-        float* dst = net->maps[outIdx];
+        float* dst = MapBuf(net, outIdx, st);
+        if (!dst) return 2;
         if (type == QCNN_CONV) rc = LaunchConv(nl.pq, cur, N, dst, fuse ? 1 : 0, st);
         else rc = LaunchFc(nl.pq, cur, N, dst, fuse ? 1 : 0, st);
         net->mapPtr[outIdx] = dst;
@@ -455,7 +475,8 @@ static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, flo
         break;
       }
       case QCNN_RELU: {
-        float* dst = net->maps[l + 1];
+        float* dst = MapBuf(net, l + 1, st);
+        if (!dst) return 2;
         rc = LaunchRelu(ctx, cur, dst, static_cast<size_t>(N) * MapElems(nl), st);
         net->mapPtr[l + 1] = dst; cur = dst; l++;
         break;
@@ -464,12 +485,14 @@ static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, flo
         const bool fuse = !net->keep && l + 1 < L && net->layers[l + 1].info.type == QCNN_POOL;
         if (fuse) {
           const NetLayer& pl = net->layers[l + 1];
-          float* dst = net->maps[l + 2];
+          float* dst = MapBuf(net, l + 2, st);
+        if (!dst) return 2;
           rc = LaunchLrnMaxPool(ctx, cur, dst, N, nl.Hin, nl.Win, nl.Cin, nl.info.lrnSiz, nl.info.lrnAlp,
                                 nl.info.lrnBet, nl.info.lrnIni, pl.info.knlSiz, pl.info.padSiz, pl.info.stride, st);
           net->mapPtr[l + 2] = dst; cur = dst; l += 2;
         } else {
-          float* dst = net->maps[l + 1];
+          float* dst = MapBuf(net, l + 1, st);
+        if (!dst) return 2;
           rc = LaunchLrn(ctx, cur, dst, static_cast<size_t>(N) * nl.Hin * nl.Win, nl.Cin, nl.info.lrnSiz,
                          nl.info.lrnAlp, nl.info.lrnBet, nl.info.lrnIni, st);
           net->mapPtr[l + 1] = dst; cur = dst; l++;
@@ -477,14 +500,16 @@ static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, flo
         break;
       }
       case QCNN_POOL: {
-        float* dst = net->maps[l + 1];
+        float* dst = MapBuf(net, l + 1, st);
+        if (!dst) return 2;
         rc = LaunchMaxPool(ctx, cur, dst, N, nl.Hin, nl.Win, nl.Cin, nl.info.knlSiz, nl.info.padSiz, nl.info.stride, st);
         net->mapPtr[l + 1] = dst; cur = dst; l++;
         break;
       }
       case QCNN_DRPT: {
         if (net->keep) {
-          float* dst = net->maps[l + 1];
+          float* dst = MapBuf(net, l + 1, st);
+        if (!dst) return 2;
           QCNN_CUDA(cudaMemcpyAsync(dst, cur, sizeof(float) * N * MapElems(nl), cudaMemcpyDeviceToDevice, st));
           net->mapPtr[l + 1] = dst; cur = dst;
         } else {
@@ -496,7 +521,8 @@ static int ForwardEager(qcnn_net* net, const float* img, int N, float* prob, flo
       case QCNN_SMAX: {
         if (logits && lastLayer)
           QCNN_CUDA(cudaMemcpyAsync(logits, cur, sizeof(float) * N * MapElems(nl), cudaMemcpyDeviceToDevice, st));
-        float* dst = lastLayer ? prob : net->maps[l + 1];
+        float* dst = lastLayer ? prob : MapBuf(net, l + 1, st);
+        if (!dst) return 2;
         rc = LaunchSoftmax(ctx, cur, dst, N, nl.Hout * nl.Wout * nl.Cout, st);
         net->mapPtr[l + 1] = dst; cur = dst; l++;
         break;

@@ -1437,8 +1437,8 @@ int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
   if (p.kernel == 6) {
     int ksteps = 0;
     for (int c = 0; c < p.g.nChunks; c++) ksteps += p.g.chunkCount[p.g.mode == 1 ? c : 0];
-    snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM) mode=%d NT=%d GT=%d slots=%d smem=%zuB grid=%d NPOS=%d "
-             "chunks=%d ksteps=%d nsplit=%d", p.g.mode, p.g.NT, p.g.GT, p.g.NSLOT, p.smem,
+    snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM%s) mode=%d NT=%d GT=%d slots=%d smem=%zuB grid=%d NPOS=%d "
+             "chunks=%d ksteps=%d nsplit=%d", p.g.lite ? ", 2 CTAs/SM" : "", p.g.mode, p.g.NT, p.g.GT, p.g.NSLOT, p.smem,
              CeilDiv(N * p.g.IB, p.g.NT) * L->grp * p.g.nct * std::max(1, p.g.nsplit), p.g.NPOS, p.g.nChunks,
              ksteps / std::max(1, p.g.nsplit), std::max(1, p.g.nsplit));
     return 0;

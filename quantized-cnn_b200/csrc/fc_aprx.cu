@@ -356,6 +356,7 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   a.srcImg = L->Din; a.dstImg = 0;
   a.IB = 1; a.PW = 1;
   a.NT = NTq;
+  a.aOff = 256; a.corr = NTq <= 128 ? 1 : 0; a.lite = 0;
   a.GT = 3; a.NSLOT = 5;
   a.nPB = 3; a.xprep = L->d_flat; a.nChunksAll = nChunksAll;
   a.planeF4 = KS * 2 * a.NT;

@@ -49,6 +49,11 @@ constexpr int kStager0 = 160;
 constexpr int kMaxSlots = 5;
 constexpr int kMaxGT = 8;        // k-steps per stage (TMEM ring: NSLOT * GT * 16 columns <= 256)
 constexpr int kRegPos = 16;     // float4 a stager thread holds in registers (convolution modes: planeF4 <= 16 * 96)
+// "lite" instantiation: TWO CTAs per SM (<= 128 registers per thread, 256 TMEM columns and ~110 KB of shared memory each),
+// so that one CTA's set-up, first-plane wait and epilogue overlap the other's MMA phase -- with one CTA per SM the tensor
+// pipe idles 35-45 % of a CTA's life (profiles/README.md).  Tiles of <= 128 positions, shorter register windows.
+constexpr int kRegPosLite = 11;
+constexpr int kMaxGTLite = 4;
 constexpr int kCbBufs = 4;      // codebook / index buffers: the decoders run ahead of the position planes
 
 __device__ __forceinline__ uint32_t SmemU32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -136,8 +141,11 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
 }
 
 // DBG: cycle counters of the three roles (QCNN_GEMM_DBG=1) -- a separate instantiation, the production kernel reads no clocks
-template <bool DBG>
-__global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs a) {
+template <bool DBG, bool LITE>
+__global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(const GemmArgs a) {
+  constexpr int RP = LITE ? kRegPosLite : kRegPos;
+  constexpr int MG = LITE ? kMaxGTLite : kMaxGT;
+  constexpr uint32_t kTmemCols = LITE ? 256u : 512u;
   extern __shared__ __align__(128) unsigned char smem[];
   const SmemMap sm = MapSmem(a);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   }
   for (int c = tid; c < 128; c += kThreads) biasS[c] = (c < CTv && split == 0) ? __ldg(a.bias + g * a.Kg + ch0 + c) : 0.0f;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmemBase)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmemBase)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmemD = *tmemBase;          // D: columns [0, NT)
-  const uint32_t tmemA = tmemD + 256;        // A ring: columns [256, 256 + NSLOT*GT*16)
+  const uint32_t tmemA = tmemD + static_cast<uint32_t>(a.aOff);   // A ring: columns [aOff, aOff + NSLOT*GT*16)
 
   const int warpU = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform role selector
   if (warpU >= 5) {
@@ -334,14 +342,14 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
     // Positions of the convolution modes: global -> registers -> hi/lo planes.  (16-byte cp.async of scattered pieces
     // costs one shared-memory wavefront per THREAD -- profiles/README.md, "staging" -- whereas a 128-bit store of 32
     // consecutive float4 costs four per warp.)  A thread owns float4 st, st+96, ...: at most kRegPos of them.
-    float4 rg[kRegPos];
-    int poffR[kRegPos];        // chunk-invariant source offset of the thread's float4 (mode 0: incl. the half's +4)
-    int prowR[kRegPos];        // mode 1: first input row (phase row 0), very negative when the column is outside
+    float4 rg[RP];
+    int poffR[RP];        // chunk-invariant source offset of the thread's float4 (mode 0: incl. the half's +4)
+    int prowR[RP];        // mode 1: first input row (phase row 0), very negative when the column is outside
     uint32_t pvalid = 0;       // mode 0: bit i = the float4 exists and its position is inside an image
     uint32_t phalf = 0;        // mode 0: bit i = second half (channels 4..7 of the chunk)
     if (a.mode != 2) {
 #pragma unroll
-      for (int i = 0; i < kRegPos; i++) {
+      for (int i = 0; i < RP; i++) {
         const int p = st + i * kStagers;
         poffR[i] = 0; prowR[i] = -(1 << 28);
         if (p < a.planeF4) {
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         else if (chA + 4 >= a.Cg) m &= ~phalf;
         const float* srcG = srcBase + g * a.Cg + chA;
 #pragma unroll
-        for (int i = 0; i < kRegPos; i++) {
+        for (int i = 0; i < RP; i++) {
           rg[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           if ((m >> i) & 1u) rg[i] = __ldg(reinterpret_cast<const float4*>(srcG + poffR[i]));
         }
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         const int ph = kcBase + kc;
         const float* srcG = srcBase + static_cast<size_t>(g) * a.Cg * a.chStride + ph * a.rowStride;
 #pragma unroll
-        for (int i = 0; i < kRegPos; i++) {
+        for (int i = 0; i < RP; i++) {
           rg[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           if (static_cast<unsigned>(prowR[i] + ph) < static_cast<unsigned>(a.Hi)) {
             const float* px = srcG + poffR[i];
@@ -417,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < kRegPos; i++) {
+        for (int i = 0; i < RP; i++) {
           const int p = st + i * kStagers;
           if (p < a.planeF4) {
             float4 hi, lo;
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
       // NT <= 128 leaves room for a second accumulator: the hi*hi products go to D, the two cross terms to D + NT, and
       // the epilogue adds them -- the tensor core's accumulation error grows with the number of chained MMAs per
       // accumulator, and the chain of the dominant term is three times shorter this way
-      const uint32_t corrOff = NT <= 128 ? static_cast<uint32_t>(NT) : 0u;
+      const uint32_t corrOff = a.corr ? static_cast<uint32_t>(NT) : 0u;
       uint32_t accCorr = 0;
       long long wBC = 0, wA = 0, tStart = (DBG ? clock64() : 0ll);
       for (int kc = 0; kc < nChunks; kc++) {
@@ -561,22 +569,22 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
         } else {
           // the stage's k-steps are independent: table entries, index bytes and codeword pieces of all of them are in
           // flight together (one decoder warp per SM sub-partition: latency, not bandwidth, paces this role)
-          int i0x[kMaxGT], i1x[kMaxGT];
+          int i0x[MG], i1x[MG];
 #pragma unroll
-          for (int i = 0; i < kMaxGT; i++) {
+          for (int i = 0; i < MG; i++) {
             if (i < n) {
               const KStep ks = tabS[e0 + s0 + i];
               i0x[i] = ks.cb0 * K + (idb[ks.idx0 * 128] >> a.kshift);
               i1x[i] = ks.cb1 * K + (idb[ks.idx1 * 128] >> a.kshift);
             }
           }
-          float4 w0[kMaxGT], w1[kMaxGT];
+          float4 w0[MG], w1[MG];
 #pragma unroll
-          for (int i = 0; i < kMaxGT; i++) {
+          for (int i = 0; i < MG; i++) {
             if (i < n) { w0[i] = cb[i0x[i]]; w1[i] = cb[i1x[i]]; }
           }
 #pragma unroll
-          for (int i = 0; i < kMaxGT; i++) {
+          for (int i = 0; i < MG; i++) {
             if (i < n) StoreWeights(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0[i], w1[i]);
           }
         }
@@ -611,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                    : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (NT <= 128) {   // second accumulator (cross terms of the 3xTF32 split)
+      if (a.corr) {   // second accumulator (cross terms of the 3xTF32 split)
         uint32_t r2[16];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -635,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "r"(512) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemD), "r"(kTmemCols) : "memory");
 }
 
 }  // namespace
@@ -643,7 +651,15 @@ __global__ void __launch_bounds__(kThreads, 1) pq_gemm_tc_kernel(const GemmArgs 
 namespace qcnn {
 
 // Candidate tilings for batch N (cost in SM-cycles, comparable with PlanConv's model): 3 MMAs of NT/2 clk per k-step.
+void AddLitePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first);
+static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands) {
+  const size_t first = cands->size();
+  PlanPqGemmFull(L, N, cands);
+  static const bool lite = !(getenv("QCNN_GEMM_LITE") && getenv("QCNN_GEMM_LITE")[0] == '0');
+  if (lite) AddLitePqGemm(L, cands, first);
+}
+static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands) {
   const int G = L->grp, Cg = L->Cin / G, Kg = L->Cout / G, taps = L->ksz * L->ksz;
   if (L->K < 1 || L->K > 256 || Kg % 16 != 0) return;
   const size_t smemMax0 = L->ctx->smem_optin ? L->ctx->smem_optin : 227 * 1024;
@@ -671,6 +687,7 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
         ga.NPOS = RoundUp(NT + ((L->ksz - 1) / st) * (PWp + 1), 8);
         ga.planeF4 = st * ga.NPOS;
         if (ga.planeF4 > kRegPos * kStagers) continue;
+        ga.aOff = 256; ga.corr = NT <= 128 ? 1 : 0; ga.lite = 0;
         ga.cbSlots = 2; ga.idRows = rowsPer * L->ksz;
         ga.nChunks = st;
         ga.K = L->K; ga.cbF4 = L->K; ga.nPB = 2;
@@ -735,6 +752,7 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
       if (ga.NPOS > 16000) continue;
       ga.planeF4 = 2 * ga.NPOS;
       if (ga.planeF4 > kRegPos * kStagers) continue;
+      ga.aOff = 256; ga.corr = NT <= 128 ? 1 : 0; ga.lite = 0;
       ga.cbSlots = 2; ga.idRows = 2 * taps;
       ga.nChunks = CeilDiv(Cg, 8);
       ga.ntab = taps;
@@ -768,14 +786,40 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
   }
 }
 
+// Two-CTAs-per-SM variants of the candidates above (see kRegPosLite): tiles of <= 128 positions whose register windows,
+// TMEM columns (accumulators + weight ring <= 256) and shared memory (two CTAs + their 1 KB reservations per SM) fit
+// twice.  The fixed part of the cost model is halved: it overlaps the neighbour CTA's MMA phase.
+void AddLitePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first) {
+  const size_t smemMax = L->ctx->smem_optin ? L->ctx->smem_optin : 227 * 1024;
+  const size_t perCtaSmem = (smemMax + 1024) / 2 - 1024 - 512;
+  const size_t n = cands->size();
+  for (size_t i = first; i < n; i++) {
+    ConvPlan p = (*cands)[i].second;
+    GemmArgs& ga = p.g;
+    if (p.kernel != 6 || ga.NT > 128 || ga.GT > kMaxGTLite || ga.planeF4 > kRegPosLite * kStagers || p.smem > perCtaSmem) continue;
+    const int ring = ga.NSLOT * ga.GT * 16;
+    ga.NSLOT = std::min(ga.NSLOT, (256 - ga.NT) / (ga.GT * 16));
+    if (ga.NSLOT < 2) continue;
+    (void)ring;
+    ga.corr = (2 * ga.NT + ga.NSLOT * ga.GT * 16 <= 256) ? 1 : 0;
+    ga.aOff = ga.corr ? 2 * ga.NT : ga.NT;
+    ga.lite = 1;
+    p.J = ga.GT + 100;     // (candidate de-duplication key: distinct from the one-CTA-per-SM twin)
+    cands->emplace_back((*cands)[i].first * 0.8, p);
+  }
+}
+
 // dynamic shared-memory limit of both instantiations: raised once per device to the opt-in maximum (not per launch,
 // which would make the limit follow whichever layer ran last -- fragile under graph capture / concurrent streams)
 static int SetSmemLimitOnce(qcnn_ctx* ctx) {
   static bool done[64] = {false};
   if (ctx->device >= 0 && ctx->device < 64 && done[ctx->device]) return 0;
   const int lim = static_cast<int>(ctx->smem_optin ? ctx->smem_optin : 227 * 1024);
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  // the lite kernel's CTAs must really pair up: ask for the largest shared-memory carve-out
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   if (ctx->device >= 0 && ctx->device < 64) done[ctx->device] = true;
   return 0;
 }
@@ -811,8 +855,9 @@ int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, floa
     QCNN_CUDA(cudaMalloc(&a.dbg, 128));
     QCNN_CUDA(cudaMemsetAsync(a.dbg, 0, 128, st));
   }
-  if (dbg) pq_gemm_tc_kernel<true><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
-  else pq_gemm_tc_kernel<false><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
+  if (dbg && !a.lite) pq_gemm_tc_kernel<true, false><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
+  else if (a.lite) pq_gemm_tc_kernel<false, true><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
+  else pq_gemm_tc_kernel<false, false><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
   QCNN_CUDA(cudaGetLastError());
   if (dbg) {
     unsigned long long h[16];
@@ -836,7 +881,7 @@ int LaunchPqGemmArgs(qcnn_ctx* ctx, const GemmArgs& a, long long blocks, cudaStr
   const size_t smem = PqGemmSmemBytes(a);
   QCNN_CHECK(blocks >= 1 && blocks <= 2147483647LL, "pq_gemm_tc: bad grid");
   if (int rc = SetSmemLimitOnce(ctx)) return rc;
-  pq_gemm_tc_kernel<false><<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(a);
+  pq_gemm_tc_kernel<false, false><<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(a);
   QCNN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -130,6 +130,9 @@ struct GemmArgs {
   int nChunksAll;               // mode 2: chunks of the whole layer (xprep indexing)
   int cbF4;                     // float4 per codebook slot (K for d % 4 == 0 pieces, K/4 for d == 1 scalars)
   int NT;                     // positions per CTA = MMA N (multiple of 16, <= 256)
+  int aOff;                   // first TMEM column of the decoded-weight ring (after the accumulator(s))
+  int corr;                   // 1: the 3xTF32 cross terms have their own accumulator at column NT (added in the epilogue)
+  int lite;                   // 1: the two-CTAs-per-SM instantiation (256 TMEM columns, short register windows)
   int NPOS;                   // staged positions per plane (NT + halo)
   int planeF4;                // float4 per staged plane set (one of hi / lo, one buffer)
   int cbSlots, idRows;        // codebook slices / index rows staged per chunk

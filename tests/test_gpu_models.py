@@ -62,12 +62,13 @@ def test_model_table_end_to_end(name, po, qcnn, ctx, tmp_path):
             logits = torch.empty((N, 1000), dtype=torch.float32, device="cuda")
             if N == 3:      # every feature map of the un-fused run
                 net.set_keep_maps(True)
-                net.forward(torch.from_numpy(img).cuda(), logits=logits)
+                prob_d = net.forward(torch.from_numpy(img).cuda(), logits=logits)   # keep alive: the last map lives in it
                 for l in range(len(layers) + 1):
                     fm = net.featmap(l, N)
                     want = np.stack([r[1][l][0] for r in ref])
                     e = close(fm.cpu().numpy().reshape(-1), want.reshape(-1))
                     assert e <= RT, (name, mode, l, e)
+                del prob_d
                 net.set_keep_maps(False)
             prob = net.forward(torch.from_numpy(img).cuda(), logits=logits).cpu().numpy()
             assert close(logits.cpu().numpy(), np.stack([r[1][len(layers) - 1][0].reshape(-1) for r in ref])) <= RT, (name, mode, N)

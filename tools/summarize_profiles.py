@@ -1,7 +1,5 @@
-"""Turns ncu captures brought back in gpurun_out/ into the small, committed summaries under profiles/.
-    python tools/summarize_profiles.py <full.ncu-rep> <launches.csv> <tag>
-full.ncu-rep : ncu --set full --clock-control none --import-source on ... tools/profile_step.py
-launches.csv : ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ... bench.py
+"""Turns the ncu captures tools/r02_capture.sh left in gpurun_out/ into the small, committed summaries under profiles/.
+    python tools/summarize_profiles.py r02
 """
 import collections
 import csv
@@ -29,7 +27,12 @@ def kernels_table(rep, out_path, title):
             ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
             ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
             ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex_pct"),
-            ("sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+            # tcgen05 work is not counted by sm__inst_executed_pipe_tensor (a handful of UTCHMMA instructions drive the pipe
+            # for thousands of cycles): the cycle-based counters below are the ones that see it
+            ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_mem_cycles_active_pct"),
+            ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor_pipe_cycles_active_pct"),
+            ("TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "tensor_hmma_cycles_active"),
+            ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "tmem_pipe_inst_pct"),
             ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
             ("sm__cycles_elapsed.avg", "sm_cycles")]
     with open(out_path, "w") as f:
@@ -136,13 +139,31 @@ def launch_list(csv_path, out_path, title):
 
 
 if __name__ == "__main__":
-    rep, launches, tag = sys.argv[1], sys.argv[2], sys.argv[3]
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    kernels_table(rep, os.path.join(ROOT, "profiles", "%s_ncu_full_b256.csv" % tag),
-                  "ncu --set full --clock-control none --import-source on; tools/profile_step.py --batch 256 (AlexNet PQ forward)")
-    traffic_json(rep, os.path.join(ROOT, "profiles", "traffic.json"))
-    stage_split(rep, os.path.join(ROOT, "profiles", "%s_stage_split_b256.md" % tag),
-                "Where the time goes inside each kernel (stall samples between barriers), from the same capture")
-    if launches and os.path.exists(launches):
-        launch_list(launches, os.path.join(ROOT, "profiles", "%s_launches_bench.csv" % tag),
-                    "ncu --metrics gpu__time_duration.sum --clock-control none; python bench.py --steps 2 --warmup 1")
+    # python tools/summarize_profiles.py <tag>  -- reads gpurun_out/<tag>_*.ncu-rep / .csv written by tools/r02_capture.sh
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+    G = os.path.join(ROOT, "gpurun_out")
+    P = os.path.join(ROOT, "profiles")
+    os.makedirs(P, exist_ok=True)
+    step = os.path.join(G, "%s_step_b256.ncu-rep" % tag)
+    gemm = os.path.join(G, "%s_pq_gemm_b256.ncu-rep" % tag)
+    chain = os.path.join(G, "%s_fc_chain_b1.ncu-rep" % tag)
+    if os.path.exists(step):
+        kernels_table(step, os.path.join(P, "%s_ncu_full_b256.csv" % tag),
+                      "ncu --set full --clock-control none; tools/profile_step.py --batch 256: every kernel of one AlexNet PQ forward pass")
+        traffic_json(step, os.path.join(P, "traffic.json"))
+    if os.path.exists(gemm):
+        kernels_table(gemm, os.path.join(P, "%s_ncu_pq_gemm_b256.csv" % tag),
+                      "ncu --set full --clock-control none --import-source on -k regex:pq_gemm_tc; conv1..conv5 at batch 256")
+        stage_split(gemm, os.path.join(P, "%s_stage_split_pq_gemm_b256.md" % tag),
+                    "pq_gemm_tc (conv1..conv5, batch 256): stall samples / instructions / shared-memory wavefronts between barriers")
+    if os.path.exists(chain):
+        kernels_table(chain, os.path.join(P, "%s_ncu_fc_chain_b1.csv" % tag),
+                      "ncu --set full --clock-control none --import-source on -k regex:fc_chain; fc6->fc7->fc8 as one launch, batch 1")
+        stage_split(chain, os.path.join(P, "%s_stage_split_fc_chain_b1.md" % tag),
+                    "fc_chain_kernel (batch 1): stall samples / instructions / shared-memory wavefronts between barriers")
+    for name, title in (("launches_bench", "ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off; "
+                         "the timed steps of `python bench.py --steps 2 --warmup 3` (batch 256)"),
+                        ("launches_b1", "same metric; one forward pass at batch 1 (tools/profile_step.py --batch 1)")):
+        src = os.path.join(G, "%s_%s.csv" % (tag, name))
+        if os.path.exists(src):
+            launch_list(src, os.path.join(P, "%s_%s.csv" % (tag, name)), title)

@@ -488,8 +488,17 @@ def run_b200_arm(args, q):
     import re
 
     def tc_macs(l):
-        m = re.search(r"pq_gemm_tc.*?NT=(\d+).*?grid=(\d+).*?ksteps=(\d+)", net.pq_layer(l).describe(B))
-        return None if not m else float(m.group(2)) * float(m.group(3)) * 3.0 * 128.0 * float(m.group(1)) * 8.0
+        # executed MACs of the launch, padding included: per k-step (8 input values) either THREE kind::tf32 MMAs of
+        # 128 x NT x 8 (3xTF32 operands) or TWO kind::f16 MMAs of 128 x NT x 16 (bf16x2 operands, the default)
+        d = net.pq_layer(l).describe(B)
+        m = re.search(r"pq_gemm_tc.*?NT=(\d+).*?grid=(\d+).*?ksteps=(\d+)", d)
+        if not m:
+            return None
+        per_kstep = 2.0 * 16.0 if "bf16x2" in d else 3.0 * 8.0
+        return float(m.group(2)) * float(m.group(3)) * per_kstep * 128.0 * float(m.group(1))
+
+    def tc_is_bf(l):
+        return "bf16x2" in net.pq_layer(l).describe(B)
     for l in pq_layers:
         tm = tc_macs(l)
         if tm:
@@ -508,7 +517,7 @@ def run_b200_arm(args, q):
     if dom_macs:
         # tf32 MMAs run at half the bf16 rate: peak = measured dense bf16 (cuBLAS, MEASURED_PEAKS.json) / 2
         bf16 = float(peaks.get("bf16_tflops", 1650.0))
-        peak_tc = bf16 / 2.0
+        peak_tc = bf16 if tc_is_bf(dom) else bf16 / 2.0     # kind::tf32 issues at half the bf16 rate
         ach = 2.0 * dom_macs / (layer_ms[dom] * 1e-3) / 1e12
         dense = {0: 105415200.0, 4: 223948800.0, 8: 149520384.0, 10: 112140288.0, 12: 74760192.0,
                  15: 37748736.0, 18: 16777216.0, 21: 4096000.0}       # dense-equivalent MACs per image
@@ -518,13 +527,13 @@ def run_b200_arm(args, q):
             "executed_TFLOPs": round(ach, 1), "useful_TFLOPs": round(useful, 1), "peak_TFLOPs": round(peak_tc, 1),
             "frac_executed": round(ach / peak_tc, 4), "frac_useful": round(useful / peak_tc, 4),
             "flops_per_launch_executed": 2.0 * dom_macs, "flops_per_launch_useful": 2.0 * dense[dom] * B,
-            "peak_source": ("MEASURED_PEAKS.json bf16_tflops / 2" if "bf16_tflops" in peaks else "fallback 1650 / 2") +
-                           " (kind::tf32 issues at half the bf16 rate; nominal at %d MHz: %.0f)" %
-                           (sm_clk, 2 * 2048 * ctx.sm_count * sm_clk * 1e6 / 1e12),
+            "operands": "bf16x2 (two kind::f16 MMAs of K = 16 per k-step)" if tc_is_bf(dom) else "3xTF32 (three kind::tf32 MMAs of K = 8 per k-step)",
+            "peak_source": ("MEASURED_PEAKS.json bf16_tflops" if "bf16_tflops" in peaks else "fallback 1650") +
+                           ("" if tc_is_bf(dom) else " / 2 (kind::tf32 issues at half the bf16 rate)"),
             "all_pq_gemm_launches": {"launches": len(all_tc),
                                      "executed_TFLOPs": round(sum(2.0 * m for m, _ in all_tc) / (sum(t for _, t in all_tc) * 1e-3) / 1e12, 1),
                                      "ms": round(float(sum(t for _, t in all_tc)), 4)},
-            "note": "executed = CTAs x k-steps x 3 (3xTF32) x 2*128*NT*8, padding included; useful = dense-equivalent MACs"}
+            "note": "executed = CTAs x k-steps x MMAs per k-step x 2*128*NT*K, padding included; useful = dense-equivalent MACs"}
     else:
         gather_peak = 32.0 * ctx.sm_count * sm_clk * 1e6       # conflict-free 4-byte shared-memory lookups per second
         roofline["gather"] = {"resource": "shared-memory gather (32 lookups/clk/SM)",
@@ -672,7 +681,7 @@ def run_b200_arm(args, q):
                   "path": "tensor_core = 0 (LUT + gather kernels; tolerance 1e-4, DESIGN.md 2)",
                   "plans": {names[l]: net.pq_layer(l).describe(B).split(" grid")[0][:60] for l in (0, 4, 8, 10, 12)}}
         for l in ALEXNET_PQ:
-            net.pq_layer(l).set_param("tensor_core", 1)
+            net.pq_layer(l).set_param("tensor_core", 2)
 
     # ---- the reference CPU path, single thread, same box, same run (rank 0, N = 1 only) ----
     cpu_baseline = None

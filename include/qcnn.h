@@ -73,9 +73,9 @@ QCNN_API int qcnn_fc_layer_set_src_nhwc(qcnn_layer* layer, int H, int W, int C);
 /* Conv only: the source is NCHW [N][C][H][W] (the API input of CaffeEva::ExecForwardPass, CaffeEva.cc:225-228). */
 QCNN_API int qcnn_conv_layer_set_src_nchw(qcnn_layer* layer, int enable);
 /* tuning overrides for tests/benchmarks: "fc_nsplit" (subspace splits, 0 = automatic; 1 reproduces the reference's
- * accumulation order exactly), "fc_tn" (images per CTA: 1, 4 or 8; 0 = automatic), "tensor_core" (1 = default: large
- * batches may run as decode-at-use GEMMs on the tensor cores, 3xTF32; 0 = LUT + gather kernels only, the fp32
- * strict-parity path -- tolerances of both in DESIGN.md);
+ * accumulation order exactly), "fc_tn" (images per CTA: 1, 4 or 8; 0 = automatic), "tensor_core" (2 = default: eligible layers
+ * run as decode-at-use GEMMs on the tensor cores with bf16x2 operands; 1 = the same GEMMs with 3xTF32 operands; 0 = LUT +
+ * gather kernels only, the fp32 strict-parity path -- tolerances of all three in DESIGN.md);
  * conv layers, for tests that must know which kernel they check: "force_kernel" (-1 none | 0 s1 | 1 roll | 2 s1_tc |
  * 3 roll_tc | 4 direct | 6 pq_gemm_tc), "gemm_nt" (positions per CTA of the pq_gemm_tc tilings, 0 = any), "autotune"
  * (0 = keep the cost model's first tiling instead of timing the candidates of the chosen family on the device) */

@@ -269,6 +269,43 @@ __global__ void fc_prep_kernel(const float* __restrict__ src, const int* __restr
   base[per + r] = lo;
 }
 
+// bf16x2 form of the same image: [tile][chunk][x1, x2][KS k-steps][NT images] rows of 16 bytes = eight consecutive
+// features as bf16 (x = x1 + x2); half the bytes of the 3xTF32 image.
+__device__ __forceinline__ uint32_t PackBf(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__global__ void fc_prep_bf_kernel(const float* __restrict__ src, const int* __restrict__ srcoff, uint4* __restrict__ dst,
+                                  int N, int Din, int NT, int KS, int nChunksAll, int tiles) {
+  const size_t per = static_cast<size_t>(KS) * NT;                           // rows per plane (x1 or x2)
+  const size_t total = static_cast<size_t>(tiles) * nChunksAll * per;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t blk = i / per;
+  const int r = static_cast<int>(i - blk * per);
+  const int ks = r / NT, n = r - ks * NT;
+  const int tile = static_cast<int>(blk / nChunksAll), chunk = static_cast<int>(blk - static_cast<size_t>(tile) * nChunksAll);
+  const int Q = tile * NT + n, f = (chunk * KS + ks) * 8;
+  float v[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  if (Q < N) {
+    const float* row = src + static_cast<size_t>(Q) * Din;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (f + j < Din) v[j] = __ldg(row + (srcoff ? __ldg(srcoff + f + j) : f + j));
+  }
+  uint32_t p1[4], p2[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    p1[j] = PackBf(v[2 * j], v[2 * j + 1]);
+    const float r0 = v[2 * j] - __uint_as_float(p1[j] << 16), r1 = v[2 * j + 1] - __uint_as_float(p1[j] & 0xFFFF0000u);
+    p2[j] = PackBf(r0, r1);
+  }
+  uint4* base = dst + blk * per * 2;
+  base[r] = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+  base[per + r] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+}
+
 template <int K, int CPT, int TN, int PF, bool PRE>
 int Launch(const FcArgs& a, dim3 grid, cudaStream_t st) {
   const size_t xpad = (static_cast<size_t>(TN) * PF * a.d + 3) & ~static_cast<size_t>(3);
@@ -336,8 +373,8 @@ void DescribeFcTc(const qcnn_layer* L, int N, char* buf, size_t cap) {
   int nsplit = std::max(1, L->ctx->sm_count / (tiles * nct));
   const int kPerSplit = RoundUp(CeilDiv(kAll, nsplit), KS);
   nsplit = CeilDiv(kAll, kPerSplit);
-  snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM) mode=2 NT=%d GT=3 slots=5 grid=%d nsplit=%d ksteps=%d",
-           NT, tiles * nsplit * nct, nsplit, kPerSplit);
+  snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM%s) mode=2 NT=%d GT=3 slots=5 grid=%d nsplit=%d ksteps=%d",
+           L->opt_tc_bf ? ", bf16x2" : "", NT, tiles * nsplit * nct, nsplit, kPerSplit);
 }
 
 int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cudaStream_t st, bool* handled) {
@@ -357,9 +394,11 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   a.IB = 1; a.PW = 1;
   a.NT = NTq;
   a.aOff = 256; a.corr = NTq <= 128 ? 1 : 0; a.lite = 0;
+  a.bf = L->opt_tc_bf ? 1 : 0; a.wide = 0;
   a.GT = 3; a.NSLOT = 5;
   a.nPB = 3; a.xprep = L->d_flat; a.nChunksAll = nChunksAll;
   a.planeF4 = KS * 2 * a.NT;
+  a.planeRows = a.bf ? KS * a.NT : a.planeF4;
   a.NPOS = a.NT;
   a.cbSlots = L->d == 1 ? 8 * KS : 2 * KS;
   a.idRows = a.cbSlots;
@@ -369,6 +408,7 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   for (int i = 0; i < KS; i++) {
     KStep& ks = a.tab[i];
     ks.bStart = 2 * i * a.NT; ks.lbo = a.NT;
+    if (a.bf) { ks.bStart = i * a.NT; ks.lbo = KS * a.NT; }   // row = (k-step, image); x2 plane = K-core-matrix 1
     if (L->d == 1) { ks.idx0 = static_cast<short>(8 * i); ks.idx1 = static_cast<short>(8 * i + 4); }
     else { ks.idx0 = static_cast<short>(2 * i); ks.idx1 = static_cast<short>(2 * i + 1); }
     ks.cb0 = ks.idx0; ks.cb1 = ks.idx1;
@@ -384,7 +424,7 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   a.relu = nsplit > 1 ? 0 : relu;
   if (PqGemmSmemBytes(a) > (ctx->smem_optin ? ctx->smem_optin : 227 * 1024)) return 0;   // before any launch / allocation
   {
-    const size_t per = static_cast<size_t>(2 * KS) * NTq;
+    const size_t per = a.bf ? static_cast<size_t>(KS) * NTq : static_cast<size_t>(2 * KS) * NTq;   // 16-byte rows per plane
     const size_t total = static_cast<size_t>(tilesq) * nChunksAll * per;
     const size_t need = total * 2 * sizeof(float4);
     if (need > L->flat_bytes) {
@@ -395,8 +435,12 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
       L->flat_bytes = need;
     }
     a.xprep = L->d_flat;
-    fc_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, L->d_srcoff, reinterpret_cast<float4*>(L->d_flat),
-                                                                            N, L->Din, NTq, KS, nChunksAll, tilesq);
+    if (a.bf)
+      fc_prep_bf_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, L->d_srcoff, reinterpret_cast<uint4*>(L->d_flat),
+                                                                                 N, L->Din, NTq, KS, nChunksAll, tilesq);
+    else
+      fc_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, L->d_srcoff, reinterpret_cast<float4*>(L->d_flat),
+                                                                              N, L->Din, NTq, KS, nChunksAll, tilesq);
     QCNN_CUDA(cudaGetLastError());
     ctx->launches++;
   }

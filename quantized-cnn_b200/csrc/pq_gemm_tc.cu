@@ -120,31 +120,71 @@ __device__ __forceinline__ void StoreWeights(uint32_t taddr, const float4 w0, co
                : "memory");
 }
 
+// ---- bf16x2 operands: v = v1 + v2 with v1 = bf16(v), v2 = bf16(v - v1) (|v - v1 - v2| <= 2^-18 |v|).  One k-step of
+// eight values is TWO kind::f16 MMAs of K = 16: [w1 | w1] . [x1 | x2] + [w2 | w2] . [x1 | x2] = (w1 + w2)(x1 + x2) --
+// all four cross terms, at the fp16/bf16 rate (twice tf32's), against three K = 8 tf32 MMAs for 3xTF32.
+__device__ __forceinline__ uint32_t PackBf16x2(float lo, float hi) {   // low 16 bits = bf16(lo), high 16 bits = bf16(hi)
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void SplitBf16x4(const float4 v, uint2& p1, uint2& p2) {
+  p1.x = PackBf16x2(v.x, v.y);
+  p1.y = PackBf16x2(v.z, v.w);
+  // residuals against the rounded pieces (exact in fp32)
+  const float rx = v.x - __uint_as_float(p1.x << 16), ry = v.y - __uint_as_float(p1.x & 0xFFFF0000u);
+  const float rz = v.z - __uint_as_float(p1.y << 16), rw = v.w - __uint_as_float(p1.y & 0xFFFF0000u);
+  p2.x = PackBf16x2(rx, ry);
+  p2.y = PackBf16x2(rz, rw);
+}
+// one k-step of decoded weights -> [w1 | w1 | w2 | w2] (8 bf16 = 4 columns each) -> 16 TMEM columns of this thread's lane
+__device__ __forceinline__ void StoreWeightsBf(uint32_t taddr, const float4 w0, const float4 w1) {
+  uint2 a1, a2, b1, b2;
+  SplitBf16x4(w0, a1, a2);
+  SplitBf16x4(w1, b1, b2);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               :: "r"(taddr),
+                  "r"(a1.x), "r"(a1.y), "r"(b1.x), "r"(b1.y), "r"(a1.x), "r"(a1.y), "r"(b1.x), "r"(b1.y),
+                  "r"(a2.x), "r"(a2.y), "r"(b2.x), "r"(b2.y), "r"(a2.x), "r"(a2.y), "r"(b2.x), "r"(b2.y)
+               : "memory");
+}
+__device__ __forceinline__ void UmmaF16Ts(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmemD), "r"(tmemA), "l"(descB),
+               "r"(idesc), "r"(accumulate) : "memory");
+}
+
 struct SmemMap {  // byte offsets inside the dynamic shared memory
-  int planes, cbs, ids, tab, posoff, posrow, outoff, bias, bars, tmem, total;
+  int planes, cbs, ids, tab, posoff, posrow, posdst, outoff, bias, bars, tmem, total;
 };
 __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   SmemMap m;
   int o = 0;
-  m.planes = o; o += a.nPB * 2 * a.planeF4 * 16;        // [buf][hi,lo][planeF4]
+  m.planes = o; o += a.nPB * 2 * a.planeRows * 16;      // [buf][hi,lo | x1,x2][planeRows] 16-byte rows
   m.cbs = o;    o += kCbBufs * a.cbSlots * a.cbF4 * 16; // [cbuf][slot][cbF4] codeword pieces (raw fp32)
   m.ids = o;    o += kCbBufs * a.idRows * 128;          // [cbuf][row][128 channels] assignment indices
   m.tab = o;    o += a.ntab * 16;
   m.posoff = o; o += a.planeF4 * 4;                     // source element offset of every staged float4 (-1: zero)
   m.posrow = o; o += a.mode == 1 ? a.planeF4 * 4 : 0;   // mode 1: first input row of the position (phase row 0)
+  m.posdst = o; o += (a.bf && a.mode != 2) ? a.planeF4 * 4 : 0;   // bf16x2: byte offset of every staged float4 inside a plane
   m.outoff = o; o += 256 * 4;                           // destination element offset of every position (-1: none)
   m.bias = o;   o += 128 * 4;
-  m.bars = o;   o += 8 * (2 * kMaxSlots + 2 * kCbBufs + 7);
+  m.bars = o;   o += 8 * (2 * kMaxSlots + 2 * kCbBufs + 9);
   m.tmem = o;   o += 16;
   m.total = o;
   return m;
 }
 
 // DBG: cycle counters of the three roles (QCNN_GEMM_DBG=1) -- a separate instantiation, the production kernel reads no clocks
-template <bool DBG, bool LITE>
-__global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(const GemmArgs a) {
-  constexpr int RP = LITE ? kRegPosLite : kRegPos;
-  constexpr int MG = LITE ? kMaxGTLite : kMaxGT;
+// WIDE: a SECOND group of four decoder warps (warps 8-11; 384 threads): the two groups take the stages alternately.  The
+// decoders -- one warp per SM sub-partition, a chain of dependent shared-memory reads, the split and a tcgen05.st per
+// k-step -- are what paces the kernel (~400 clk per k-step against 384 clk of 3xTF32 MMAs or 256 clk of bf16x2 MMAs).
+template <bool DBG, bool LITE, bool BF, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(const GemmArgs a) {
+  constexpr int NTHR = WIDE ? 384 : kThreads;
+  constexpr int RP = (LITE || WIDE) ? kRegPosLite : kRegPos;
+  constexpr int MG = LITE ? kMaxGTLite : (WIDE ? 5 : kMaxGT);
   constexpr uint32_t kTmemCols = LITE ? 256u : 512u;
   extern __shared__ __align__(128) unsigned char smem[];
   const SmemMap sm = MapSmem(a);
@@ -157,13 +197,14 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
   KStep* tabS = reinterpret_cast<KStep*>(smem + sm.tab);
   int* posoff = reinterpret_cast<int*>(smem + sm.posoff);
   int* posrow = reinterpret_cast<int*>(smem + sm.posrow);
+  int* posdst = reinterpret_cast<int*>(smem + sm.posdst);
   int* outoff = reinterpret_cast<int*>(smem + sm.outoff);
   float* biasS = reinterpret_cast<float*>(smem + sm.bias);
   uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + sm.bars);   // [kMaxSlots] decoders -> issuer
   uint64_t* emptyA = fullA + kMaxSlots;                            // [kMaxSlots] MMAs retired -> decoders
-  uint64_t* fullB = emptyA + kMaxSlots;                            // [2] position planes: stagers -> issuer
-  uint64_t* emptyB = fullB + 3;                                    // [<=3] chunk's MMAs retired -> stagers
-  uint64_t* fullC = emptyB + 3;                                    // [kCbBufs] codebook + indices: stagers -> decoders
+  uint64_t* fullB = emptyA + kMaxSlots;                            // [<=4] position planes: stagers -> issuer
+  uint64_t* emptyB = fullB + 4;                                    // [<=4] chunk's MMAs retired -> stagers
+  uint64_t* fullC = emptyB + 4;                                    // [kCbBufs] codebook + indices: stagers -> decoders
   uint64_t* emptyC = fullC + kCbBufs;                              // [kCbBufs] decoders done with the chunk -> stagers
   uint64_t* doneBar = emptyC + kCbBufs;
   uint32_t* tmemBase = reinterpret_cast<uint32_t*>(smem + sm.tmem);
@@ -192,8 +233,8 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
     dstBase = a.partial + (static_cast<size_t>(split) * a.N + i0) * a.dstImg + g * a.Kg + ch0;
 
   // ---- set-up (all threads) ----
-  for (int e = tid; e < a.ntab; e += kThreads) tabS[e] = a.tab[e];
-  for (int p = tid; p < a.planeF4; p += kThreads) {
+  for (int e = tid; e < a.ntab; e += NTHR) tabS[e] = a.tab[e];
+  for (int p = tid; p < a.planeF4; p += NTHR) {
     int off = -1;
     if (a.mode == 0) {
       // float4 p: half = p / NPOS, position = p % NPOS; the half only selects the channel offset (added per chunk)
@@ -215,8 +256,14 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
       posrow[p] = colOk ? r * a.stride - a.pad : -(1 << 28);
     }
     posoff[p] = off;   // (mode 2 stages its planes by bulk copy: no offsets)
+    if (BF && a.mode != 2) {
+      // bf16x2 planes hold 16-byte rows of eight values: mode 0 row = position, the half selects bytes 0-7 / 8-15;
+      // mode 1 row = (phase-column pair, position), the column's parity selects the half
+      const int grp = p / a.NPOS, pos = p - grp * a.NPOS;
+      posdst[p] = a.mode == 0 ? pos * 16 + grp * 8 : ((grp >> 1) * a.NPOS + pos) * 16 + (grp & 1) * 8;
+    }
   }
-  for (int p = tid; p < 256; p += kThreads) {
+  for (int p = tid; p < 256; p += NTHR) {
     int off = -1;
     if (p < NT) {
       const int Q = Q0 + p;
@@ -227,15 +274,15 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
     }
     outoff[p] = off;
   }
-  for (int c = tid; c < 128; c += kThreads) biasS[c] = (c < CTv && split == 0) ? __ldg(a.bias + g * a.Kg + ch0 + c) : 0.0f;
+  for (int c = tid; c < 128; c += NTHR) biasS[c] = (c < CTv && split == 0) ? __ldg(a.bias + g * a.Kg + ch0 + c) : 0.0f;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmemBase)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
     for (int i = 0; i < kMaxSlots; i++) { MbarInit(fullA + i, kDecoders); MbarInit(emptyA + i, 1); }
-    for (int i = 0; i < 3; i++) { MbarInit(fullB + i, kStagers); MbarInit(emptyB + i, 1); }
-    for (int i = 0; i < kCbBufs; i++) { MbarInit(fullC + i, kStagers); MbarInit(emptyC + i, kDecoders); }
+    for (int i = 0; i < 4; i++) { MbarInit(fullB + i, kStagers); MbarInit(emptyB + i, 1); }
+    for (int i = 0; i < kCbBufs; i++) { MbarInit(fullC + i, kStagers); MbarInit(emptyC + i, WIDE ? 2 * kDecoders : kDecoders); }
     MbarInit(doneBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -246,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
   const uint32_t tmemA = tmemD + static_cast<uint32_t>(a.aOff);   // A ring: columns [aOff, aOff + NSLOT*GT*16)
 
   const int warpU = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform role selector
-  if (warpU >= 5) {
+  if (warpU >= 5 && warpU < 8) {
     // =========================== stagers ===========================
     const int st = tid - kStager0;
     // chunk kc: codebook slices + index rows by cp.async (one group); the positions travel through registers
@@ -409,14 +456,14 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
       c0 = (DBG ? clock64() : 0ll);
       if (kc >= a.nPB) MbarWait(emptyB + buf, ((kc / a.nPB) - 1) & 1);   // planes last read by the MMAs of chunk kc-nPB
       sEB += (DBG ? clock64() : 0ll) - c0;
-      float4* pHi = planes + (buf * 2 + 0) * a.planeF4;
-      float4* pLo = planes + (buf * 2 + 1) * a.planeF4;
+      float4* pHi = planes + (buf * 2 + 0) * a.planeRows;
+      float4* pLo = planes + (buf * 2 + 1) * a.planeRows;
       if (a.mode == 2) {
         // the plane image of (tile, chunk) was written by fc_prep_kernel: one bulk copy (hi + lo, contiguous) straight
         // into the planes, completion counted on the same mbarrier the stagers arrive on
         if (st == 0) {
-          const uint32_t bytes = static_cast<uint32_t>(a.planeF4) * 32u;
-          const float* gsrc = a.xprep + (static_cast<size_t>(tile) * a.nChunksAll + (k0 / a.chunkCount[0] + kc)) * a.planeF4 * 8;
+          const uint32_t bytes = static_cast<uint32_t>(a.planeRows) * 32u;
+          const float* gsrc = a.xprep + (static_cast<size_t>(tile) * a.nChunksAll + (k0 / a.chunkCount[0] + kc)) * a.planeRows * 8;
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemU32(fullB + buf)), "r"(bytes) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(SmemU32(pHi)), "l"(gsrc), "r"(bytes), "r"(SmemU32(fullB + buf)) : "memory");
@@ -428,10 +475,18 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
         for (int i = 0; i < RP; i++) {
           const int p = st + i * kStagers;
           if (p < a.planeF4) {
-            float4 hi, lo;
-            SplitTf32x4(rg[i], hi, lo);
-            pHi[p] = hi;
-            pLo[p] = lo;
+            if (BF) {
+              uint2 p1, p2;
+              SplitBf16x4(rg[i], p1, p2);
+              const int db = posdst[p];
+              *reinterpret_cast<uint2*>(reinterpret_cast<char*>(pHi) + db) = p1;
+              *reinterpret_cast<uint2*>(reinterpret_cast<char*>(pLo) + db) = p2;
+            } else {
+              float4 hi, lo;
+              SplitTf32x4(rg[i], hi, lo);
+              pHi[p] = hi;
+              pLo[p] = lo;
+            }
           }
         }
       }
@@ -462,7 +517,9 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
     //  this form the SASS issues them back to back -- profiles/README.md, "MMA issue".)
     {
       // instruction descriptor: D = F32, A = B = TF32, K-major, N = NT, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) | (8u << 24);
+      // (bf16x2: A = B = BF16, format code 1; same N / M fields)
+      const uint32_t idesc = BF ? ((1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) | (8u << 24))
+                                : ((1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) | (8u << 24));
       const uint64_t descFixed = (static_cast<uint64_t>(8) << 32) | (static_cast<uint64_t>(1) << 46);  // SBO = 128 B
       const uint32_t planes0 = SmemU32(planes);
       int t = 0;
@@ -479,8 +536,8 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
         MbarWait(fullB + buf, (kc / a.nPB) & 1);
         wBC += (DBG ? clock64() : 0ll) - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t dHi = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 0) * a.planeF4) * 16u) >> 4) & 0x3FFFu);
-        const uint64_t dLo = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 1) * a.planeF4) * 16u) >> 4) & 0x3FFFu);
+        const uint64_t dHi = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 0) * a.planeRows) * 16u) >> 4) & 0x3FFFu);
+        const uint64_t dLo = descFixed | (((planes0 + static_cast<uint32_t>((buf * 2 + 1) * a.planeRows) * 16u) >> 4) & 0x3FFFu);
         const int e0 = a.chunkFirst[a.mode == 1 ? kcBase + kc : 0];
         const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kcBase + kc : 0];
         for (int s0 = 0; s0 < ne; s0 += GT, t++) {
@@ -496,9 +553,16 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
               const uint64_t off = static_cast<uint64_t>(static_cast<uint32_t>(ks.bStart)) |
                                    (static_cast<uint64_t>(static_cast<uint32_t>(ks.lbo)) << 16);
               const uint32_t aHi = tmemA + static_cast<uint32_t>((slot * GT + i) * 16), aLo = aHi + 8;
-              UmmaTf32Ts(tmemD, aHi, dHi + off, idesc, acc);
-              UmmaTf32Ts(tmemD + corrOff, aHi, dLo + off, idesc, corrOff ? accCorr : 1u);
-              UmmaTf32Ts(tmemD + corrOff, aLo, dHi + off, idesc, 1u);
+              if (BF) {
+                // B = [x1 | x2]: K-core-matrix 0 in the first plane, 1 in the second (the table's lbo is the plane distance);
+                // A = [w1 | w1] then [w2 | w2] (columns 0-7 / 8-15 of the slot)
+                UmmaF16Ts(tmemD, aHi, dHi + off, idesc, acc);
+                UmmaF16Ts(tmemD + corrOff, aLo, dHi + off, idesc, corrOff ? accCorr : 1u);
+              } else {
+                UmmaTf32Ts(tmemD, aHi, dHi + off, idesc, acc);
+                UmmaTf32Ts(tmemD + corrOff, aHi, dLo + off, idesc, corrOff ? accCorr : 1u);
+                UmmaTf32Ts(tmemD + corrOff, aLo, dHi + off, idesc, 1u);
+              }
               acc = 1u;
               accCorr = 1u;
             }
@@ -527,9 +591,10 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
     }
   } else {
     // =========================== decoders ===========================
-    const int c = tid;                              // channel row = TMEM lane
+    const int c = (warp & 3) * 32 + lane;           // channel row = TMEM lane (a warp reaches the lanes of its sub-partition)
     const int cc = min(c, CTv - 1);                 // rows beyond the valid channels decode a copy (never stored)
-    const uint32_t laneBase = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t laneBase = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int grp = (WIDE && warp >= 8) ? 1 : 0;    // WIDE: group 0 decodes the even stages, group 1 the odd ones
     int t = 0;
     long long dFC = 0, dEA = 0, dT0 = (DBG ? clock64() : 0ll);
     for (int kc = 0; kc < nChunks; kc++) {
@@ -543,6 +608,7 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
       const int e0 = a.chunkFirst[a.mode == 1 ? kcBase + kc : 0];
       const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kcBase + kc : 0];
       for (int s0 = 0; s0 < ne; s0 += GT, t++) {
+        if (WIDE && (t & 1) != grp) continue;
         const int slot = t % NSLOT;
         if (t >= NSLOT) {
           c0 = (DBG ? clock64() : 0ll);
@@ -564,7 +630,8 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
             w0.z = c0p[2 * K + (r0[256] >> a.kshift)]; w0.w = c0p[3 * K + (r0[384] >> a.kshift)];
             w1.x = c1p[r1[0] >> a.kshift];           w1.y = c1p[K + (r1[128] >> a.kshift)];
             w1.z = c1p[2 * K + (r1[256] >> a.kshift)]; w1.w = c1p[3 * K + (r1[384] >> a.kshift)];
-            StoreWeights(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0, w1);
+            if (BF) StoreWeightsBf(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0, w1);
+            else StoreWeights(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0, w1);
           }
         } else {
           // the stage's k-steps are independent: table entries, index bytes and codeword pieces of all of them are in
@@ -585,7 +652,10 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
           }
 #pragma unroll
           for (int i = 0; i < MG; i++) {
-            if (i < n) StoreWeights(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0[i], w1[i]);
+            if (i < n) {
+              if (BF) StoreWeightsBf(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0[i], w1[i]);
+              else StoreWeights(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0[i], w1[i]);
+            }
           }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -605,12 +675,12 @@ __global__ void __launch_bounds__(kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(cons
   MbarWait(doneBar, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   {
-    const int q = warp & 3, hsel = warp >> 2;
+    const int q = warp & 3, hsel = warp >> 2;     // (warps 4-7 and, WIDE, 8-11 take the other position blocks)
     const int c = q * 32 + lane;
     const bool chOk = c < CTv;
     const float bv = biasS[c];
     const int nblk = NT >> 4;   // 16-position blocks
-    for (int blk = hsel; blk < nblk; blk += 2) {
+    for (int blk = hsel; blk < nblk; blk += NTHR / 128) {
       uint32_t r[16];
       const uint32_t taddr = tmemD + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(blk * 16);
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -652,12 +722,20 @@ namespace qcnn {
 
 // Candidate tilings for batch N (cost in SM-cycles, comparable with PlanConv's model): 3 MMAs of NT/2 clk per k-step.
 void AddLitePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first);
+void AddWidePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first);
 static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands) {
   const size_t first = cands->size();
   PlanPqGemmFull(L, N, cands);
   static const bool lite = !(getenv("QCNN_GEMM_LITE") && getenv("QCNN_GEMM_LITE")[0] == '0');
-  if (lite) AddLitePqGemm(L, cands, first);
+  static const bool wide = !(getenv("QCNN_GEMM_WIDE") && getenv("QCNN_GEMM_WIDE")[0] == '0');
+  const size_t mid = cands->size();
+  if (wide) AddWidePqGemm(L, cands, first);
+  if (lite) {
+    const size_t end = cands->size();
+    AddLitePqGemm(L, cands, first);
+    (void)mid; (void)end;
+  }
 }
 static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands) {
   const int G = L->grp, Cg = L->Cin / G, Kg = L->Cout / G, taps = L->ksz * L->ksz;
@@ -688,9 +766,15 @@ static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<dou
         ga.planeF4 = st * ga.NPOS;
         if (ga.planeF4 > kRegPos * kStagers) continue;
         ga.aOff = 256; ga.corr = NT <= 128 ? 1 : 0; ga.lite = 0;
+        ga.bf = L->opt_tc_bf ? 1 : 0;
+        if (ga.bf && (st & 1)) continue;       // bf16x2 rows hold a PAIR of phase columns
+        ga.planeRows = ga.bf ? (st / 2) * ga.NPOS : ga.planeF4;
         ga.cbSlots = 2; ga.idRows = rowsPer * L->ksz;
         ga.nChunks = st;
         ga.K = L->K; ga.cbF4 = L->K; ga.nPB = 2;
+        // bf16x2 planes are half the size: keep EVERY phase row of the tile resident (no plane reuse), so that the stagers
+        // never wait for the MMAs and the few k-steps of a phase row (conv1: 16-18) are not what hides a global-load latency
+        if (ga.bf && st <= 4) ga.nPB = st;
         ga.nct = CeilDiv(Kg, 128);
         int ne = 0;
         for (int ph = 0; ph < st; ph++) {
@@ -699,9 +783,14 @@ static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<dou
             for (int kw = 0; kw < L->ksz; kw += 2, ne++) {
               if (ne >= kMaxKSteps) { ne = kMaxKSteps + 1000; break; }
               KStep& ks = ga.tab[ne];
-              const bool paired = kw + 1 < L->ksz && (kw % st) + 1 < st;   // partner in the next phase column, same shift
+              // partner in the next phase column, same shift (bf16x2: the partner must be the odd column of the same pair)
+              const bool paired = kw + 1 < L->ksz && (kw % st) + 1 < st && !(ga.bf && ((kw % st) & 1));
               ks.bStart = (kw % st) * ga.NPOS + (kh / st) * PWp + kw / st;
               ks.lbo = paired ? ga.NPOS : 1;
+              if (ga.bf) {   // row = (pair of phase columns, position); K-core-matrix 1 = the x2 plane
+                ks.bStart = ((kw % st) >> 1) * ga.NPOS + (kh / st) * PWp + kw / st;
+                ks.lbo = ga.planeRows;
+              }
               ks.idx0 = static_cast<short>((kh - ph) / st * L->ksz + kw);
               ks.idx1 = static_cast<short>(paired ? ks.idx0 + 1 : ks.idx0);
               ks.cb0 = 0; ks.cb1 = paired ? 0 : 1;
@@ -753,6 +842,8 @@ static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<dou
       ga.planeF4 = 2 * ga.NPOS;
       if (ga.planeF4 > kRegPos * kStagers) continue;
       ga.aOff = 256; ga.corr = NT <= 128 ? 1 : 0; ga.lite = 0;
+      ga.bf = L->opt_tc_bf ? 1 : 0;
+      ga.planeRows = ga.bf ? ga.NPOS : ga.planeF4;   // (bf16x2: lbo = NPOS rows is the x1 -> x2 plane distance as well)
       ga.cbSlots = 2; ga.idRows = 2 * taps;
       ga.nChunks = CeilDiv(Cg, 8);
       ga.ntab = taps;
@@ -789,6 +880,21 @@ static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<dou
 // Two-CTAs-per-SM variants of the candidates above (see kRegPosLite): tiles of <= 128 positions whose register windows,
 // TMEM columns (accumulators + weight ring <= 256) and shared memory (two CTAs + their 1 KB reservations per SM) fit
 // twice.  The fixed part of the cost model is halved: it overlaps the neighbour CTA's MMA phase.
+// Twelve-warp variants (second decoder group): stages of <= 5 k-steps, register windows of the lite size.
+void AddWidePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first) {
+  (void)L;
+  const size_t n = cands->size();
+  for (size_t i = first; i < n; i++) {
+    ConvPlan p = (*cands)[i].second;
+    GemmArgs& ga = p.g;
+    if (p.kernel != 6 || ga.lite || ga.GT > 5 || ga.planeF4 > kRegPosLite * kStagers || ga.NSLOT < 2) continue;
+    ga.wide = 1;
+    p.threads = 384;
+    p.J = ga.GT + 200;     // (candidate de-duplication key)
+    cands->emplace_back((*cands)[i].first * 0.85, p);
+  }
+}
+
 void AddLitePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first) {
   const size_t smemMax = L->ctx->smem_optin ? L->ctx->smem_optin : 227 * 1024;
   const size_t perCtaSmem = (smemMax + 1024) / 2 - 1024 - 512;
@@ -796,7 +902,7 @@ void AddLitePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>
   for (size_t i = first; i < n; i++) {
     ConvPlan p = (*cands)[i].second;
     GemmArgs& ga = p.g;
-    if (p.kernel != 6 || ga.NT > 128 || ga.GT > kMaxGTLite || ga.planeF4 > kRegPosLite * kStagers || p.smem > perCtaSmem) continue;
+    if (p.kernel != 6 || ga.wide || ga.NT > 128 || ga.GT > kMaxGTLite || ga.planeF4 > kRegPosLite * kStagers || p.smem > perCtaSmem) continue;
     const int ring = ga.NSLOT * ga.GT * 16;
     ga.NSLOT = std::min(ga.NSLOT, (256 - ga.NT) / (ga.GT * 16));
     if (ga.NSLOT < 2) continue;
@@ -815,11 +921,14 @@ static int SetSmemLimitOnce(qcnn_ctx* ctx) {
   static bool done[64] = {false};
   if (ctx->device >= 0 && ctx->device < 64 && done[ctx->device]) return 0;
   const int lim = static_cast<int>(ctx->smem_optin ? ctx->smem_optin : 227 * 1024);
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  // the lite kernel's CTAs must really pair up: ask for the largest shared-memory carve-out
-  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#define QCNN_SMEM_ATTR(...) QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim))
+  QCNN_SMEM_ATTR(false, false, false, false); QCNN_SMEM_ATTR(true, false, false, false); QCNN_SMEM_ATTR(false, true, false, false);
+  QCNN_SMEM_ATTR(false, false, true, false);  QCNN_SMEM_ATTR(true, false, true, false);  QCNN_SMEM_ATTR(false, true, true, false);
+  QCNN_SMEM_ATTR(false, false, false, true);  QCNN_SMEM_ATTR(false, false, true, true);  QCNN_SMEM_ATTR(true, false, true, true);
+#undef QCNN_SMEM_ATTR
+  // the lite kernels' CTAs must really pair up: ask for the largest shared-memory carve-out
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false, true, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false, true, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   if (ctx->device >= 0 && ctx->device < 64) done[ctx->device] = true;
   return 0;
 }
@@ -855,9 +964,19 @@ int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, floa
     QCNN_CUDA(cudaMalloc(&a.dbg, 128));
     QCNN_CUDA(cudaMemsetAsync(a.dbg, 0, 128, st));
   }
-  if (dbg && !a.lite) pq_gemm_tc_kernel<true, false><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
-  else if (a.lite) pq_gemm_tc_kernel<false, true><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
-  else pq_gemm_tc_kernel<false, false><<<static_cast<unsigned>(blocks), kThreads, p.smem, st>>>(a);
+  const unsigned nb = static_cast<unsigned>(blocks);
+  if (a.wide) {
+    if (a.bf) { if (dbg) pq_gemm_tc_kernel<true, false, true, true><<<nb, 384, p.smem, st>>>(a); else pq_gemm_tc_kernel<false, false, true, true><<<nb, 384, p.smem, st>>>(a); }
+    else pq_gemm_tc_kernel<false, false, false, true><<<nb, 384, p.smem, st>>>(a);
+  } else if (a.bf) {
+    if (dbg && !a.lite) pq_gemm_tc_kernel<true, false, true, false><<<nb, kThreads, p.smem, st>>>(a);
+    else if (a.lite) pq_gemm_tc_kernel<false, true, true, false><<<nb, kThreads, p.smem, st>>>(a);
+    else pq_gemm_tc_kernel<false, false, true, false><<<nb, kThreads, p.smem, st>>>(a);
+  } else {
+    if (dbg && !a.lite) pq_gemm_tc_kernel<true, false, false, false><<<nb, kThreads, p.smem, st>>>(a);
+    else if (a.lite) pq_gemm_tc_kernel<false, true, false, false><<<nb, kThreads, p.smem, st>>>(a);
+    else pq_gemm_tc_kernel<false, false, false, false><<<nb, kThreads, p.smem, st>>>(a);
+  }
   QCNN_CUDA(cudaGetLastError());
   if (dbg) {
     unsigned long long h[16];
@@ -881,7 +1000,8 @@ int LaunchPqGemmArgs(qcnn_ctx* ctx, const GemmArgs& a, long long blocks, cudaStr
   const size_t smem = PqGemmSmemBytes(a);
   QCNN_CHECK(blocks >= 1 && blocks <= 2147483647LL, "pq_gemm_tc: bad grid");
   if (int rc = SetSmemLimitOnce(ctx)) return rc;
-  pq_gemm_tc_kernel<false, false><<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(a);
+  if (a.bf) pq_gemm_tc_kernel<false, false, true, false><<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(a);
+  else pq_gemm_tc_kernel<false, false, false, false><<<static_cast<unsigned>(blocks), kThreads, smem, st>>>(a);
   QCNN_CUDA(cudaGetLastError());
   return 0;
 }

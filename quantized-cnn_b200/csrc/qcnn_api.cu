@@ -2,6 +2,7 @@
 // CaffeEva::PrepCtrdBuf / PrepAsmtBuf, reference src/CaffeEva.cc:534-623), per-layer forward calls, file formats.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -104,6 +105,10 @@ static qcnn_layer* NewLayer(qcnn_ctx* ctx, int kind) {
   memset(static_cast<void*>(L), 0, sizeof(*L));
   L->ctx = ctx;
   L->kind = kind;
+  // default operand format of the tensor-core GEMMs: bf16x2 (two MMAs per k-step at twice the tf32 rate; measured error
+  // at the level of 3xTF32's); tensor_core = 1 or QCNN_TC_BF=0 selects 3xTF32
+  static const bool bfDefault = !(getenv("QCNN_TC_BF") && getenv("QCNN_TC_BF")[0] == '0');
+  L->opt_tc_bf = bfDefault ? 1 : 0;
   return L;
 }
 
@@ -244,6 +249,7 @@ int qcnn_layer_set_param(qcnn_layer* L, const char* name, int value) {
     // 0: LUT + gather kernels only (fp32 adds in the reference's association; the strict-parity path);
     // 1 (default): large batches may use the decode-at-use tensor-core GEMMs (3xTF32, wider tolerance: DESIGN.md)
     L->opt_no_tc = value ? 0 : 1;
+    L->opt_tc_bf = value == 2 ? 1 : 0;   // 2: bf16x2 operands (two MMAs per k-step at the bf16 rate) instead of 3xTF32
     L->plan_N = 0; L->tuned = 0;
     if (L->tunedPlans) L->tunedPlans->clear();
   }

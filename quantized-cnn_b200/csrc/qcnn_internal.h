@@ -133,6 +133,10 @@ struct GemmArgs {
   int aOff;                   // first TMEM column of the decoded-weight ring (after the accumulator(s))
   int corr;                   // 1: the 3xTF32 cross terms have their own accumulator at column NT (added in the epilogue)
   int lite;                   // 1: the two-CTAs-per-SM instantiation (256 TMEM columns, short register windows)
+  int wide;                   // 1: the twelve-warp instantiation (second decoder warp group)
+  int bf;                     // 1: bf16x2 operands (x = x1 + x2, w = w1 + w2 as bf16 pieces; TWO kind::f16 MMAs of K = 16 per
+                              //    k-step: [w1|w1].[x1|x2] + [w2|w2].[x1|x2]) instead of 3xTF32 (three kind::tf32 MMAs of K = 8)
+  int planeRows;              // 16-byte rows per staged plane (3xTF32: planeF4; bf16x2: positions x k-step groups)
   int NPOS;                   // staged positions per plane (NT + halo)
   int planeF4;                // float4 per staged plane set (one of hi / lo, one buffer)
   int cbSlots, idRows;        // codebook slices / index rows staged per chunk
@@ -188,6 +192,7 @@ struct qcnn_layer {
   int opt_fc_nsplit;
   int opt_fc_tn;
   int opt_no_tc;         // 1: never use the decode-at-use tensor-core kernels for this layer
+  int opt_tc_bf;         // 1: the tensor-core kernels take bf16x2 operands (tensor_core = 2) instead of 3xTF32
   int opt_force_kernel;  // conv: 1 + kernel id the plan is restricted to (0 = none); tests pin the kernel they check
   int opt_no_autotune;   // conv: 1 = keep the cost model's first tiling (no on-device timing)
   int opt_gemm_nt;       // conv: restrict pq_gemm_tc tilings to this many positions per CTA (0 = any)

@@ -103,6 +103,12 @@ def test_fc_tc_parity(case, po, qcnn, ctx):
     assert close(y, ref) <= RTOL_TC, close(y, ref)
     yr = layer.forward(xd, relu=True).cpu().numpy()
     assert close(yr, np.maximum(ref, 0)) <= RTOL_TC
+    assert "bf16x2" in layer.describe(N)       # the default operand format
+    layer.set_param("tensor_core", 1)          # 3xTF32 operands
+    assert "bf16x2" not in layer.describe(N)
+    yb = layer.forward(xd).cpu().numpy()
+    assert close(yb, ref) <= RTOL_TC, close(yb, ref)
+    layer.set_param("tensor_core", 2)
     # explicit single split keeps the gather kernel and the reference's accumulation order: bit-exact
     layer.set_param("fc_nsplit", 1)
     assert np.array_equal(layer.forward(xd).cpu().numpy(), ref)
@@ -199,6 +205,11 @@ def test_conv_parity(case, po, qcnn, ctx):
         yn = layer.forward(torch.from_numpy(po.nhwc_to_nchw(x)).cuda()).cpu().numpy()
         assert close(yn, ref) <= RTOL_TC, close(yn, ref)
         layer.set_src_nchw(False)
+    # (a2) both operand formats of the tensor-core GEMM explicitly: 2 = bf16x2 (the default), 1 = 3xTF32
+    for tc in (2, 1):
+        layer.set_param("tensor_core", tc)
+        yb = layer.forward(xd).cpu().numpy()
+        assert close(yb, ref) <= RTOL_TC, (tc, close(yb, ref), layer.describe(N))
     # (b) strict parity: LUT + gather kernels only (fp32 adds)
     layer.set_param("tensor_core", 0)
     y = layer.forward(xd).cpu().numpy()

@@ -82,8 +82,9 @@ def test_conv_layer_b256_pinned_kernel(name, po, qcnn, ctx):
     ref = np.concatenate(par(lambda i: po.conv_aprx(x[i:i + 1], L, ctrd, asmt, bias), range(N)))
     layer = qcnn.ConvLayer(ctx, Cin, Hi, Wi, Cout, k, pad, stride, G, ctrd, asmt, bias)
     xd = torch.from_numpy(x).cuda()
-    for kern, nt in [(6, 256), (6, 128)] + [(k_, 0) for k_ in PINS[name] if k_ != 6]:
-        layer.set_param("tensor_core", 1 if kern == 6 else 0)
+    # tensor_core: 1 = 3xTF32 operands, 2 = bf16x2 operands (two MMAs per k-step), 0 = LUT + gather kernels
+    for kern, nt, tc in [(6, 256, 1), (6, 128, 1), (6, 256, 2), (6, 128, 2)] + [(k_, 0, 0) for k_ in PINS[name] if k_ != 6]:
+        layer.set_param("tensor_core", tc)
         layer.set_param("force_kernel", kern)
         layer.set_param("gemm_nt", nt)
         y = layer.forward(xd).cpu().numpy()
@@ -92,8 +93,10 @@ def test_conv_layer_b256_pinned_kernel(name, po, qcnn, ctx):
         if kern == 6:
             # NT=256: ONE TMEM accumulator (all 3xTF32 terms chained in it); NT=128: the cross terms have their own
             assert "NT=%d" % nt in desc and "nsplit=1" in desc, desc
+            assert ("bf16x2" in desc) == (tc == 2), desc
         a, b = e1(y, ref), close(y, ref)
-        REPORT["%s/N=256/%s%s" % (name, KNAME[kern], "/NT=%d" % nt if nt else "")] = {"e1_max1ref": a, "e2_close": b, "plan": desc}
+        REPORT["%s/N=256/%s%s%s" % (name, KNAME[kern], "/NT=%d" % nt if nt else "", "/bf16x2" if tc == 2 else "")] = {
+            "e1_max1ref": a, "e2_close": b, "plan": desc}
         assert b <= (RTOL_TC if kern == 6 else RTOL), (name, kern, nt, b)
         assert a <= (E1_TC if kern == 6 else E1_STRICT), (name, kern, nt, a)
         yr = layer.forward(xd, relu=True).cpu().numpy()

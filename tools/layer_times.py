@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--reps", type=int, default=30)
+    ap.add_argument("--tc", type=int, default=-1, help="tensor_core parameter for every PQ layer (0 strict, 1 3xTF32, 2 bf16x2)")
     args = ap.parse_args()
     import torch
     q = importlib.import_module("quantized-cnn_b200")
@@ -24,6 +25,10 @@ def main():
     ctx = q.Context(0)
     net = q.Net(ctx, d, pfx, "AlexNet")
     B = args.batch
+    if args.tc >= 0:
+        for l in range(net.layer_count):
+            if net.pq_layer(l) is not None:
+                net.pq_layer(l).set_param("tensor_core", args.tc)
     img = torch.from_numpy(bench.lcg_images(B, 12345)).cuda()
     prob = torch.empty((B, 1000), dtype=torch.float32, device="cuda")
     for _ in range(5):

@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--tc", type=int, default=-1, help="tensor_core parameter for every PQ layer")
     args = ap.parse_args()
     import torch
     q = importlib.import_module("quantized-cnn_b200")
@@ -24,6 +25,10 @@ def main():
     d, pfx, what = bench.model_files(q, tmp)
     ctx = q.Context(0)
     net = q.Net(ctx, d, pfx, "AlexNet")
+    if args.tc >= 0:
+        for l in range(net.layer_count):
+            if net.pq_layer(l) is not None:
+                net.pq_layer(l).set_param("tensor_core", args.tc)
     img = torch.from_numpy(bench.lcg_images(args.batch, 12345)).cuda()
     prob = torch.empty((args.batch, 1000), dtype=torch.float32, device="cuda")
     for l in range(net.layer_count):

@@ -617,6 +617,13 @@ def run_b200_arm(args, q):
             rec("fc6", fcs[:1], [1], xin)
             rec("fc7", fcs[1:2], [1], torch.rand((1, 4096), dtype=torch.float32, device=dev))
             rec("fc8", fcs[2:], [0], torch.rand((1, 4096), dtype=torch.float32, device=dev))
+            # the same kernel on a layer large enough to amortise its fixed latencies (launch, first bytes, one cross-CTA
+            # reduction): 8192 subspaces x 4096 outputs, K = 32, d = 4 -> 33.5 MB of assignments + 4.2 MB of codebook
+            rs2 = np.random.RandomState(5)
+            big = q.FcLayer(ctx, 32768, (rs2.randn(8192, 32, 4) * 0.01).astype(np.float32),
+                            rs2.randint(0, 32, size=(4096, 8192)).astype(np.uint8), np.zeros(4096, np.float32))
+            rec("synthetic fc 32768 -> 4096 (S=8192, K=32, d=4)", [big], [0], torch.rand((1, 32768), dtype=torch.float32, device=dev))
+            big.close()
         except q.QcnnError as e:          # shapes the fused kernel does not take: say so instead of a number
             fc_b1["error"] = str(e)
         extra["fc_b1"] = fc_b1

@@ -85,12 +85,14 @@ __device__ __forceinline__ void MbarArrive(uint64_t* b) {
 __device__ __forceinline__ void MbarExpectTx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemU32(b)), "r"(bytes) : "memory");
 }
+// bounded spin: a protocol error traps (launch failure) instead of hanging the GPU
 __device__ __forceinline__ void MbarWait(uint64_t* b, uint32_t parity) {
-  uint32_t ok;
-  do {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; spins++) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(SmemU32(b)), "r"(parity) : "memory");
-  } while (!ok);
+    if (spins > (1u << 26)) __trap();
+  }
 }
 __device__ __forceinline__ void BulkLoad(void* smemDst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -150,11 +152,12 @@ __device__ __forceinline__ float CollectSlice(float* partial, int pitch, int G, 
       else v[j] = make_uint4(0u, 0u, 0u, 0u);
     }
     // words not written yet are polled again TOGETHER: one round trip after the slowest producer, not one per word
-    for (;;) {
+    for (uint32_t spins = 0;; spins++) {
       bool pend = false;
 #pragma unroll
       for (int j = 0; j < NP; j++) pend = pend || Pending(v[j]);
       if (!pend) break;
+      if (spins > (1u << 22)) __trap();     // seconds: a producer that never publishes is a bug, not something to wait for
 #pragma unroll
       for (int j = 0; j < NP; j++)
         if (Pending(v[j])) v[j] = LdRelaxed4(base + j * dp);
@@ -367,9 +370,9 @@ __global__ void __launch_bounds__(kThreads, 1) fc_chain_kernel(const __grid_cons
       }
     }
     if (lane == 0) {
-      if (a.dbg) {   // measurement only: when the first 8 chunks landed ([24 + i]); valid while the ring is not recycled
+      if (a.dbg) {   // measurement only: when the first 8 chunks landed ([24 + i]); only while the ring is not recycled
         a.dbg[32 * cta + 23] = clock64();   // all copies issued
-        for (int i = 0; i < min(issued, min(8, a.nStage)); i++) {
+        for (int i = 0; i < (issued <= a.nStage ? min(issued, 8) : 0); i++) {
           MbarWait(fullB + i, 0);
           a.dbg[32 * cta + 24 + i] = clock64();
         }

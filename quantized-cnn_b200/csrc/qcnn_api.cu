@@ -109,6 +109,9 @@ static qcnn_layer* NewLayer(qcnn_ctx* ctx, int kind) {
   // at the level of 3xTF32's); tensor_core = 1 or QCNN_TC_BF=0 selects 3xTF32
   static const bool bfDefault = !(getenv("QCNN_TC_BF") && getenv("QCNN_TC_BF")[0] == '0');
   L->opt_tc_bf = bfDefault ? 1 : 0;
+  // process-wide default of "tensor_core": QCNN_NO_DECTC=1 starts every layer on the strict LUT + gather path
+  static const bool strictDefault = getenv("QCNN_NO_DECTC") != nullptr;
+  L->opt_no_tc = strictDefault ? 1 : 0;
   return L;
 }
 

@@ -35,6 +35,7 @@ CHAINS = [
     ([(128, 64, 16, 256, 8), (64, 520, 16, 16, 4), (520, 40, 130, 32, 4), (40, 24, 40, 16, 1)], [0, 1, 1, 1]),  # 4 layers
     ([(2048, 6000, 512, 32, 4)], [1]),                                 # 16 channels per thread (Dout > 4096)
     ([(640, 2500, 320, 64, 2)], [0]),                                  # 8 channels per thread, d = 2
+    ([(28416, 4096, 7104, 32, 4), (4096, 520, 1024, 32, 4)], [1, 0]),  # 48 rows x 4 KB per CTA: the ring is recycled
 ]
 
 

@@ -138,6 +138,42 @@ def launch_list(csv_path, out_path, title):
             f.write('"%s","%s","%s",%d,%.1f,%.2f,%.1f\n' % (k.replace(",", ";"), g, b, len(v), sum(v) / 1e3, 100 * sum(v) / tot, sum(v) / len(v) / 1e3))
 
 
+def step_metrics(csv_path, out_path, traffic_path):
+    """ncu --metrics ... --csv log of one forward pass (long format: one row per launch and metric) -> one row per launch;
+    DRAM bytes per launch of the PQ / LRN kernels -> traffic.json (read by bench.py for `roofline.traffic`)."""
+    import json
+    lines = [l for l in open(csv_path) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        key = (row["ID"], row["Kernel Name"])
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except (KeyError, ValueError):
+            continue
+        unit = row.get("Metric Unit", "").lower()
+        v *= {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "usecond": 1e3, "msecond": 1e6, "second": 1e9}.get(unit, 1.0)   # bytes / ns
+        per.setdefault(key, collections.OrderedDict())[row["Metric Name"]] = v
+    names = []
+    for d in per.values():
+        for k in d:
+            if k not in names:
+                names.append(k)
+    with open(out_path, "w") as f:
+        f.write("# ncu --metrics ... --clock-control none; tools/profile_step.py --batch 256: every kernel of one AlexNet PQ forward pass (bytes, ns)\n")
+        f.write("kernel," + ",".join(names) + "\n")
+        for (_, k), d in per.items():
+            f.write('"%s",' % k.replace("void <unnamed>::", "").replace("<unnamed>::", "").replace(",", ";")[:64] +
+                    ",".join("%.6g" % d.get(n, float("nan")) for n in names) + "\n")
+    order = ["conv1", "lrn1+pool1", "conv2", "lrn2+pool2", "conv3", "conv4", "conv5", "fc6", "fc7", "fc8"]
+    out, i = {}, 0
+    for (_, k), d in per.items():
+        if "reduce" in k or "fc_prep" in k or "maxpool_kernel" in k or "softmax" in k or "u8hwc" in k or i >= len(order):
+            continue
+        out[order[i]] = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+        i += 1
+    json.dump(out, open(traffic_path, "w"), indent=1)
+
+
 if __name__ == "__main__":
     # python tools/summarize_profiles.py <tag>  -- reads gpurun_out/<tag>_*.ncu-rep / .csv written by tools/r02_capture.sh
     tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
@@ -151,6 +187,9 @@ if __name__ == "__main__":
         kernels_table(step, os.path.join(P, "%s_ncu_full_b256.csv" % tag),
                       "ncu --set full --clock-control none; tools/profile_step.py --batch 256: every kernel of one AlexNet PQ forward pass")
         traffic_json(step, os.path.join(P, "traffic.json"))
+    stepm = os.path.join(G, "%s_step_b256_metrics.csv" % tag)
+    if os.path.exists(stepm):
+        step_metrics(stepm, os.path.join(P, "%s_step_b256_metrics.csv" % tag), os.path.join(P, "traffic.json"))
     if os.path.exists(gemm):
         kernels_table(gemm, os.path.join(P, "%s_ncu_pq_gemm_b256.csv" % tag),
                       "ncu --set full --clock-control none --import-source on -k regex:pq_gemm_tc; conv1..conv5 at batch 256")

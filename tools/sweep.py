@@ -91,7 +91,7 @@ def main():
                     full = layer.describe(N)
                     desc = full.split(" ")[0].split("(")[0]
                     m = re.search(r"pq_gemm_tc.*?NT=(\d+).*?grid=(\d+).*?ksteps=(\d+)", full)
-                    tfl = 2.0 * float(m.group(2)) * float(m.group(3)) * 3 * 128 * float(m.group(1)) * 8 / (t * 1e-3) / 1e12 if m else 0.0
+                    tfl = 2.0 * float(m.group(2)) * float(m.group(3)) * (2 * 16 if "bf16x2" in full else 3 * 8) * 128 * float(m.group(1)) / (t * 1e-3) / 1e12 if m else 0.0
                     rows.append("%s,%d,%d,%d,%d,%.4f,%.2f,%.1f,%.4f,%.3e,%.4f,%.1f,%.2e,%.2e,%s" % (
                         name, S, K, d, N, t, w["alg_bytes"] / 1e6, w["alg_bytes"] / (t * 1e-3) / 1e9,
                         w["alg_bytes"] / (t * 1e-3) / 1e9 / hbm, w["lookups"] / (t * 1e-3),

@@ -1416,6 +1416,10 @@ int LaunchConv(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
         ms = std::min(ms, t);
       }
       if (!ok) continue;
+      static const bool tuneLog = getenv("QCNN_AUTOTUNE_LOG") != nullptr;
+      if (tuneLog)
+        fprintf(stderr, "[qcnn autotune] N=%d Cout=%d k=%d cand %zu: kernel=%d NT/CPT=%d GT/J=%d lite=%d wide=%d bf=%d nsplit=%d smem=%zu -> %.4f ms\n",
+                N, L->Cout, L->ksz, i, c.kernel, c.CPT, c.kernel == 6 ? c.g.GT : c.J, c.g.lite, c.g.wide, c.g.bf, c.g.nsplit, c.smem, ms);
       if (ms < bestMs) { bestMs = ms; bestI = i; }
     }
     cudaEventDestroy(e0);

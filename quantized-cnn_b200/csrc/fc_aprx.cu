@@ -395,6 +395,7 @@ int LaunchFcTc(qcnn_layer* L, const float* src, int N, float* dst, int relu, cud
   a.NT = NTq;
   a.aOff = 256; a.corr = NTq <= 128 ? 1 : 0; a.lite = 0;
   a.bf = L->opt_tc_bf ? 1 : 0; a.wide = 0;
+  if (a.bf && L->d_ctrd_bf) { a.ctrd = reinterpret_cast<const float*>(L->d_ctrd_bf); a.cbPre = 1; }   // (d % 4 == 0)
   a.GT = 3; a.NSLOT = 5;
   a.nPB = 3; a.xprep = L->d_flat; a.nChunksAll = nChunksAll;
   a.planeF4 = KS * 2 * a.NT;

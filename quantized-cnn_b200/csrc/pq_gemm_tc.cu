@@ -137,11 +137,19 @@ __device__ __forceinline__ void SplitBf16x4(const float4 v, uint2& p1, uint2& p2
   p2.x = PackBf16x2(rx, ry);
   p2.y = PackBf16x2(rz, rw);
 }
-// one k-step of decoded weights -> [w1 | w1 | w2 | w2] (8 bf16 = 4 columns each) -> 16 TMEM columns of this thread's lane
+// one k-step of decoded weights -> [w1 | w1 | w2 | w2] (8 bf16 = 4 columns each) -> 16 TMEM columns of this thread's lane.
+// PRE: the staged codebook already holds {w1, w2} per 4-float piece (qcnn_layer::d_ctrd_bf, split once at layer creation):
+// the decoders convert nothing; otherwise split here.
+template <bool PRE>
 __device__ __forceinline__ void StoreWeightsBf(uint32_t taddr, const float4 w0, const float4 w1) {
   uint2 a1, a2, b1, b2;
-  SplitBf16x4(w0, a1, a2);
-  SplitBf16x4(w1, b1, b2);
+  if (PRE) {
+    a1 = make_uint2(__float_as_uint(w0.x), __float_as_uint(w0.y)); a2 = make_uint2(__float_as_uint(w0.z), __float_as_uint(w0.w));
+    b1 = make_uint2(__float_as_uint(w1.x), __float_as_uint(w1.y)); b2 = make_uint2(__float_as_uint(w1.z), __float_as_uint(w1.w));
+  } else {
+    SplitBf16x4(w0, a1, a2);
+    SplitBf16x4(w1, b1, b2);
+  }
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
                "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                :: "r"(taddr),
@@ -153,6 +161,15 @@ __device__ __forceinline__ void UmmaF16Ts(uint32_t tmemD, uint32_t tmemA, uint64
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmemD), "r"(tmemA), "l"(descB),
                "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void split_codebook_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, size_t n) {
+  const size_t gs = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += gs) {
+    uint2 p1, p2;
+    SplitBf16x4(src[i], p1, p2);
+    dst[i] = make_uint4(p1.x, p1.y, p2.x, p2.y);
+  }
 }
 
 struct SmemMap {  // byte offsets inside the dynamic shared memory
@@ -522,7 +539,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
                                 : ((1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) | (8u << 24));
       const uint64_t descFixed = (static_cast<uint64_t>(8) << 32) | (static_cast<uint64_t>(1) << 46);  // SBO = 128 B
       const uint32_t planes0 = SmemU32(planes);
-      int t = 0;
+      int t = 0, islot = 0, iround = 0;
       uint32_t acc = 0;
       // NT <= 128 leaves room for a second accumulator: the hi*hi products go to D, the two cross terms to D + NT, and
       // the epilogue adds them -- the tensor core's accumulation error grows with the number of chained MMAs per
@@ -541,9 +558,10 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
         const int e0 = a.chunkFirst[a.mode == 1 ? kcBase + kc : 0];
         const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kcBase + kc : 0];
         for (int s0 = 0; s0 < ne; s0 += GT, t++) {
-          const int slot = t % NSLOT;
+          const int slot = islot;                         // = t % NSLOT, ring round = t / NSLOT (kept incrementally)
           c0 = (DBG ? clock64() : 0ll);
-          MbarWait(fullA + slot, (t / NSLOT) & 1);
+          MbarWait(fullA + slot, iround & 1);
+          if (++islot == NSLOT) { islot = 0; iround++; }
           wA += (DBG ? clock64() : 0ll) - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int n = min(GT, ne - s0);
@@ -595,7 +613,8 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
     const int cc = min(c, CTv - 1);                 // rows beyond the valid channels decode a copy (never stored)
     const uint32_t laneBase = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int grp = (WIDE && warp >= 8) ? 1 : 0;    // WIDE: group 0 decodes the even stages, group 1 the odd ones
-    int t = 0;
+    const bool pre = BF && a.cbPre != 0;
+    int t = 0, dslot = 0, dround = 0;
     long long dFC = 0, dEA = 0, dT0 = (DBG ? clock64() : 0ll);
     for (int kc = 0; kc < nChunks; kc++) {
       const int cbuf = kc % kCbBufs;
@@ -608,11 +627,12 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
       const int e0 = a.chunkFirst[a.mode == 1 ? kcBase + kc : 0];
       const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kcBase + kc : 0];
       for (int s0 = 0; s0 < ne; s0 += GT, t++) {
+        const int slot = dslot, round = dround;           // = t % NSLOT, t / NSLOT (kept incrementally: no divisions)
+        if (++dslot == NSLOT) { dslot = 0; dround++; }
         if (WIDE && (t & 1) != grp) continue;
-        const int slot = t % NSLOT;
-        if (t >= NSLOT) {
+        if (round > 0) {
           c0 = (DBG ? clock64() : 0ll);
-          MbarWait(emptyA + slot, ((t / NSLOT) - 1) & 1);
+          MbarWait(emptyA + slot, (round - 1) & 1);
           dEA += (DBG ? clock64() : 0ll) - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
@@ -630,7 +650,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
             w0.z = c0p[2 * K + (r0[256] >> a.kshift)]; w0.w = c0p[3 * K + (r0[384] >> a.kshift)];
             w1.x = c1p[r1[0] >> a.kshift];           w1.y = c1p[K + (r1[128] >> a.kshift)];
             w1.z = c1p[2 * K + (r1[256] >> a.kshift)]; w1.w = c1p[3 * K + (r1[384] >> a.kshift)];
-            if (BF) StoreWeightsBf(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0, w1);
+            if (BF) StoreWeightsBf<false>(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0, w1);
             else StoreWeights(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0, w1);
           }
         } else {
@@ -653,7 +673,8 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
 #pragma unroll
           for (int i = 0; i < MG; i++) {
             if (i < n) {
-              if (BF) StoreWeightsBf(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0[i], w1[i]);
+              if (BF && pre) StoreWeightsBf<true>(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0[i], w1[i]);
+              else if (BF) StoreWeightsBf<false>(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0[i], w1[i]);
               else StoreWeights(tmemA + laneBase + static_cast<uint32_t>((slot * GT + i) * 16), w0[i], w1[i]);
             }
           }
@@ -933,9 +954,23 @@ static int SetSmemLimitOnce(qcnn_ctx* ctx) {
   return 0;
 }
 
+// bf16x2 form of the codebook, made once per layer: every aligned 4-float piece becomes {w1 (4 x bf16), w2 (4 x bf16)},
+// same indexing and size as the fp32 codebook
+int BuildCtrdBf(qcnn_layer* L) {
+  if (L->d % 4 != 0 || L->d_ctrd_bf) return 0;
+  const size_t n = static_cast<size_t>(L->S) * L->K * L->d / 4;
+  QCNN_CUDA(cudaMalloc(&L->d_ctrd_bf, n * sizeof(uint4)));
+  split_codebook_kernel<<<static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 1024)), 256>>>(
+      reinterpret_cast<const float4*>(L->d_ctrd), reinterpret_cast<uint4*>(L->d_ctrd_bf), n);
+  QCNN_CUDA(cudaGetLastError());
+  QCNN_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
 int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, float* dst, int relu, cudaStream_t st) {
   GemmArgs a = p.g;
   a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
+  if (a.bf && L->d_ctrd_bf) { a.ctrd = reinterpret_cast<const float*>(L->d_ctrd_bf); a.cbPre = 1; }
   a.N = N; a.relu = a.nsplit > 1 ? 0 : relu;
   if (a.nsplit < 1) a.nsplit = 1;
   a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;

@@ -170,6 +170,7 @@ int qcnn_conv_layer_create(qcnn_ctx* ctx, int Cin, int Hin, int Win, int Cout, i
     qcnn_layer_destroy(L);
     return 2;
   }
+  if (BuildCtrdBf(L)) { qcnn_layer_destroy(L); return 2; }
   if (PlanConv(L, 256)) {  // validates that a tiling exists; re-planned per batch size at launch
     qcnn_layer_destroy(L);
     return 1;
@@ -213,6 +214,7 @@ int qcnn_fc_layer_create(qcnn_ctx* ctx, int Din, int Dout, int S, int K, int d, 
     qcnn_layer_destroy(L);
     return 2;
   }
+  if (BuildCtrdBf(L)) { qcnn_layer_destroy(L); return 2; }
   *out = L;
   return 0;
 }
@@ -293,6 +295,7 @@ void qcnn_layer_destroy(qcnn_layer* L) {
   if (L->d_partial) cudaFree(L->d_partial);
   if (L->d_flat) cudaFree(L->d_flat);
   if (L->d_cpart) cudaFree(L->d_cpart);
+  if (L->d_ctrd_bf) cudaFree(L->d_ctrd_bf);
   if (L->d_srcoff) cudaFree(L->d_srcoff);
   delete L->cands;
   delete L->tunedPlans;

@@ -136,6 +136,7 @@ struct GemmArgs {
   int wide;                   // 1: the twelve-warp instantiation (second decoder warp group)
   int bf;                     // 1: bf16x2 operands (x = x1 + x2, w = w1 + w2 as bf16 pieces; TWO kind::f16 MMAs of K = 16 per
                               //    k-step: [w1|w1].[x1|x2] + [w2|w2].[x1|x2]) instead of 3xTF32 (three kind::tf32 MMAs of K = 8)
+  int cbPre;                  // 1: `ctrd` is the pre-split codebook (qcnn_layer::d_ctrd_bf): the decoders convert nothing
   int planeRows;              // 16-byte rows per staged plane (3xTF32: planeF4; bf16x2: positions x k-step groups)
   int NPOS;                   // staged positions per plane (NT + halo)
   int planeF4;                // float4 per staged plane set (one of hi / lo, one buffer)
@@ -186,6 +187,7 @@ struct qcnn_layer {
   size_t partial_bytes;
   float* d_flat;         // tensor-core FC path: source pre-split into hi/lo plane images (fc_prep_kernel)
   size_t flat_bytes;
+  void* d_ctrd_bf;        // codebook pre-split into bf16 pieces (pq_gemm_tc.cu, bf16x2 operands): per 4-float piece {w1 (4 x bf16), w2 (4 x bf16)}
   float* d_cpart;        // chain kernel (fc_chain.cu): per-CTA partial sums [sm_count][DoutPad], words double as ready flags
   size_t cpart_bytes;
   // tuning overrides (0 = automatic)
@@ -213,6 +215,7 @@ int LaunchFcChain(qcnn_ctx* ctx, qcnn_layer* const* layers, const int* relu, int
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
 size_t PqGemmSmemBytes(const GemmArgs& a);
 int LaunchPqGemmArgs(qcnn_ctx* ctx, const GemmArgs& a, long long blocks, cudaStream_t st);
+int BuildCtrdBf(qcnn_layer* L);   // layer creation: the bf16x2 form of the codebook (d % 4 == 0)
 int LaunchSplitReduce(qcnn_ctx* ctx, const float* partial, float* dst, int rows, int cols, int colsPad, int nsplit, int relu,
                       cudaStream_t st);
 void DescribeFcTc(const qcnn_layer* L, int N, char* buf, size_t cap);

@@ -163,13 +163,27 @@ __device__ __forceinline__ void UmmaF16Ts(uint32_t tmemD, uint32_t tmemA, uint64
                "r"(idesc), "r"(accumulate) : "memory");
 }
 
-__global__ void split_codebook_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, size_t n) {
+// fp32 codebook [S][K][P pieces of 4 floats] -> [S][P][K] x {w1, w2}: the K pieces of one (subspace, piece) are contiguous
+__global__ void split_codebook_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, int S, int K, int P) {
+  const size_t n = static_cast<size_t>(S) * K * P;
   const size_t gs = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += gs) {
+    const int pc = static_cast<int>(i % P);
+    const size_t sk = i / P;
+    const int k = static_cast<int>(sk % K);
+    const size_t sidx = sk / K;
     uint2 p1, p2;
     SplitBf16x4(src[i], p1, p2);
-    dst[i] = make_uint4(p1.x, p1.y, p2.x, p2.y);
+    dst[(sidx * P + pc) * K + k] = make_uint4(p1.x, p1.y, p2.x, p2.y);
   }
+}
+
+// byte t (< 32) of the 32 bytes {lo, hi} held in registers (t is warp-uniform: selects, no local memory)
+__device__ __forceinline__ int ByteOf32(const uint4 lo, const uint4 hi, int t) {
+  const uint32_t x = (t & 16) ? hi.x : lo.x, y = (t & 16) ? hi.y : lo.y, z = (t & 16) ? hi.z : lo.z, w = (t & 16) ? hi.w : lo.w;
+  const uint32_t xy = (t & 4) ? y : x, zw = (t & 4) ? w : z;
+  const uint32_t v = (t & 8) ? zw : xy;
+  return static_cast<int>((v >> ((t & 3) * 8)) & 0xFFu);
 }
 
 struct SmemMap {  // byte offsets inside the dynamic shared memory
@@ -181,7 +195,7 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   m.planes = o; o += a.nPB * 2 * a.planeRows * 16;      // [buf][hi,lo | x1,x2][planeRows] 16-byte rows
   m.cbs = o;    o += kCbBufs * a.cbSlots * a.cbF4 * 16; // [cbuf][slot][cbF4] codeword pieces (raw fp32)
   m.ids = o;    o += kCbBufs * a.idRows * 128;          // [cbuf][row][128 channels] assignment indices
-  m.tab = o;    o += a.ntab * 16;
+  m.tab = o;                                            // (the k-step table is read from the kernel parameters)
   m.posoff = o; o += a.planeF4 * 4;                     // source element offset of every staged float4 (-1: zero)
   m.posrow = o; o += a.mode == 1 ? a.planeF4 * 4 : 0;   // mode 1: first input row of the position (phase row 0)
   m.posdst = o; o += (a.bf && a.mode != 2) ? a.planeF4 * 4 : 0;   // bf16x2: byte offset of every staged float4 inside a plane
@@ -211,7 +225,6 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
   float4* planes = reinterpret_cast<float4*>(smem + sm.planes);
   float4* cbs = reinterpret_cast<float4*>(smem + sm.cbs);
   uint8_t* ids = smem + sm.ids;
-  KStep* tabS = reinterpret_cast<KStep*>(smem + sm.tab);
   int* posoff = reinterpret_cast<int*>(smem + sm.posoff);
   int* posrow = reinterpret_cast<int*>(smem + sm.posrow);
   int* posdst = reinterpret_cast<int*>(smem + sm.posdst);
@@ -250,7 +263,6 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
     dstBase = a.partial + (static_cast<size_t>(split) * a.N + i0) * a.dstImg + g * a.Kg + ch0;
 
   // ---- set-up (all threads) ----
-  for (int e = tid; e < a.ntab; e += NTHR) tabS[e] = a.tab[e];
   for (int p = tid; p < a.planeF4; p += NTHR) {
     int off = -1;
     if (a.mode == 0) {
@@ -299,7 +311,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
   if (tid == 0) {
     for (int i = 0; i < kMaxSlots; i++) { MbarInit(fullA + i, kDecoders); MbarInit(emptyA + i, 1); }
     for (int i = 0; i < 4; i++) { MbarInit(fullB + i, kStagers); MbarInit(emptyB + i, 1); }
-    for (int i = 0; i < kCbBufs; i++) { MbarInit(fullC + i, kStagers); MbarInit(emptyC + i, WIDE ? 2 * kDecoders : kDecoders); }
+    for (int i = 0; i < kCbBufs; i++) { MbarInit(fullC + i, a.bulkC ? 1 : kStagers); MbarInit(emptyC + i, WIDE ? 2 * kDecoders : kDecoders); }
     MbarInit(doneBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -313,6 +325,11 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
   if (warpU >= 5 && warpU < 8) {
     // =========================== stagers ===========================
     const int st = tid - kStager0;
+    // 4-float piece j0/4 of codeword k of subspace s: fp32 codebook [S][K][d] or the pre-split one [S][d/4][K][4 words]
+    auto piece = [&](int s, int j0, int k) -> const float* {
+      return a.cbPre ? a.ctrd + ((static_cast<size_t>(s) * (a.d >> 2) + (j0 >> 2)) * K + k) * 4
+                     : a.ctrd + (static_cast<size_t>(s) * K + k) * a.d + j0;
+    };
     // chunk kc: codebook slices + index rows by cp.async (one group); the positions travel through registers
     auto fetchChunk = [&](int kc) {
       const int cbuf = kc % kCbBufs;
@@ -325,16 +342,46 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
         const int sB = okB ? chB / a.d : 0, jB = okB ? chB - sB * a.d : 0;
         // (positions travel through registers: loadPos / storePos)
         // codebook slices: slot = half
-        const float* cA = a.ctrd + static_cast<size_t>(sA) * K * a.d + jA;
-        const float* cB = a.ctrd + static_cast<size_t>(sB) * K * a.d + jB;
         float4* cdst = cbs + cbuf * a.cbSlots * K;
+        if (a.bulkC) {
+          // four bulk copies (two contiguous codebook slices, two contiguous index blocks), completion counted on fullC;
+          // a half beyond the group's channels stages valid data (its positions are staged as zeros)
+          if (st == 0) {
+            const uint32_t cbBytes = static_cast<uint32_t>(K) * 16u, idBytes = static_cast<uint32_t>(CTv * a.tapsPad);
+            const uint32_t bar = SmemU32(fullC + cbuf);
+            uint8_t* idst = ids + cbuf * a.idRows * 128;
+            const uint8_t* tA = a.asmtT + (static_cast<size_t>(g * a.S + sA) * a.KgPad + ch0) * a.tapsPad;
+            const uint8_t* tB = a.asmtT + (static_cast<size_t>(g * a.S + sB) * a.KgPad + ch0) * a.tapsPad;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * cbBytes + 2u * idBytes) : "memory");
+#define QCNN_BULK(dst, src, bytes) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" \
+                                                ::"r"(SmemU32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory")
+            QCNN_BULK(cdst, piece(sA, jA, 0), cbBytes);
+            QCNN_BULK(cdst + K, piece(sB, jB, 0), cbBytes);
+            QCNN_BULK(idst, tA, idBytes);
+            QCNN_BULK(idst + 128 * a.tapsPad, tB, idBytes);
+#undef QCNN_BULK
+          }
+          return;
+        }
         for (int k = st; k < K; k += kStagers) {
-          CpAsync16(cdst + k, cA + static_cast<size_t>(k) * a.d, okA);
-          CpAsync16(cdst + K + k, cB + static_cast<size_t>(k) * a.d, okB);
+          CpAsync16(cdst + k, piece(sA, jA, k), okA);
+          CpAsync16(cdst + K + k, piece(sB, jB, k), okB);
+        }
+        if (a.idxT) {
+          // channel-major index block [half][channel][tapsPad]: contiguous CTv * tapsPad bytes per half
+          const int gran = (CTv * a.tapsPad) >> 4;
+          const uint8_t* tA = a.asmtT + (static_cast<size_t>(g * a.S + sA) * a.KgPad + ch0) * a.tapsPad;
+          const uint8_t* tB = a.asmtT + (static_cast<size_t>(g * a.S + sB) * a.KgPad + ch0) * a.tapsPad;
+          uint8_t* idst = ids + cbuf * a.idRows * 128;
+          for (int e = st; e < 2 * gran; e += kStagers) {
+            const bool hb = e >= gran;
+            const int q = hb ? e - gran : e;
+            CpAsync16(idst + (hb ? 128 * a.tapsPad : 0) + (q << 4), (hb ? tB : tA) + (static_cast<size_t>(q) << 4), true);
+          }
         }
         // index rows [half][tap]: stager warp w takes rows w, w+3, ...; lane < gran copies one 16-byte granule
         const int gran = CTv >> 4;
-        if (lane < gran) {
+        if (!a.idxT && lane < gran) {
           const uint8_t* asA = a.asmt + static_cast<size_t>(g * a.S + sA) * taps * a.KgPad + ch0 + (lane << 4);
           const uint8_t* asB = a.asmt + static_cast<size_t>(g * a.S + sB) * taps * a.KgPad + ch0 + (lane << 4);
           uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
@@ -352,7 +399,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
         // codebook: slot 0 = the first 4 floats of every codeword of subspace 0, slot 1 = zeros (unpaired taps)
         float4* cdst = cbs + cbuf * a.cbSlots * K;
         for (int k = st; k < K; k += kStagers) {
-          CpAsync16(cdst + k, a.ctrd + static_cast<size_t>(k) * a.d, true);
+          CpAsync16(cdst + k, piece(0, 0, k), true);
           CpAsync16(cdst + K + k, a.ctrd, false);
         }
         // index rows of the taps with kh % stride == ph, in (kh, kw) order
@@ -390,7 +437,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
             const int q = e / K, k = e - q * K;
             const int f = f0 + 4 * q;
             const int s = f / a.d, j0 = f - s * a.d;
-            CpAsync16(cdst + e, a.ctrd + (static_cast<size_t>(s) * K + k) * a.d + j0, true);
+            CpAsync16(cdst + e, piece(s, j0, k), true);
           }
           if (lane < gran) {
             uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
@@ -458,18 +505,97 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
         }
       }
     };
+    long long sCp = 0, sEB = 0, sEC = 0, sT0 = (DBG ? clock64() : 0ll);
+    // Twelve-warp tiles of 3x3 layers (<= 6 float4 per stager thread, chunks of 9 k-steps): TWO register sets, the loads of
+    // chunk kc+2 are issued right after the stores of chunk kc, so a global-load latency (~1-1.5 k clk under load) overlaps
+    // a whole chunk instead of being waited for in every iteration -- with one set the stagers, not the MMAs, paced these
+    // layers (role counters: 3.8 k clk per chunk against 2.4 k clk of MMAs).
+    constexpr int H = 6;
+    const bool dbl = WIDE && a.mode == 0 && a.planeF4 <= H * kStagers;
+    if (WIDE && dbl) {
+      float4 rg2[WIDE ? H : 1];
+      int pdst[WIDE ? H : 1];           // bf16x2: byte offset of the element inside a plane (chunk-invariant)
+#pragma unroll
+      for (int i = 0; i < H; i++) {
+        const int p = st + i * kStagers;
+        const int grp = p >= a.NPOS ? 1 : 0;
+        pdst[i] = (p - grp * a.NPOS) * 16 + grp * 8;
+      }
+      auto loadH = [&](int kc, auto& r) {
+        const int chA = (kcBase + kc) * 8;
+        uint32_t m = pvalid;
+        if (chA >= a.Cg) m = 0;
+        else if (chA + 4 >= a.Cg) m &= ~phalf;
+        const float* srcG = srcBase + g * a.Cg + chA;
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+          r[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if ((m >> i) & 1u) r[i] = __ldg(reinterpret_cast<const float4*>(srcG + poffR[i]));
+        }
+      };
+      auto iter = [&](int kc, auto& r) {
+        const int buf = kc % a.nPB;
+        long long c0 = (DBG ? clock64() : 0ll);
+        if (!a.bulkC) {
+          if (kc + 1 < nChunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else CpAsyncWaitAll();
+          sCp += (DBG ? clock64() : 0ll) - c0;
+          MbarArrive(fullC + kc % kCbBufs);
+        }
+        c0 = (DBG ? clock64() : 0ll);
+        if (kc >= a.nPB) MbarWait(emptyB + buf, ((kc / a.nPB) - 1) & 1);
+        sEB += (DBG ? clock64() : 0ll) - c0;
+        float4* pHi = planes + (buf * 2 + 0) * a.planeRows;
+        float4* pLo = planes + (buf * 2 + 1) * a.planeRows;
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+          const int p = st + i * kStagers;
+          if (p < a.planeF4) {
+            if (BF) {
+              uint2 p1, p2;
+              SplitBf16x4(r[i], p1, p2);
+              *reinterpret_cast<uint2*>(reinterpret_cast<char*>(pHi) + pdst[i]) = p1;
+              *reinterpret_cast<uint2*>(reinterpret_cast<char*>(pLo) + pdst[i]) = p2;
+            } else {
+              float4 hi, lo;
+              SplitTf32x4(r[i], hi, lo);
+              pHi[p] = hi;
+              pLo[p] = lo;
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        MbarArrive(fullB + buf);
+        if (kc + 2 < nChunks) {
+          loadH(kc + 2, r);
+          const int nb = (kc + 2) % kCbBufs;
+          c0 = (DBG ? clock64() : 0ll);
+          if (kc + 2 >= kCbBufs) MbarWait(emptyC + nb, (((kc + 2) / kCbBufs) - 1) & 1);
+          sEC += (DBG ? clock64() : 0ll) - c0;
+          fetchChunk(kc + 2);
+        }
+      };
+      fetchChunk(0);
+      loadH(0, rg);
+      if (nChunks > 1) { fetchChunk(1); loadH(1, rg2); }
+      for (int kc = 0; kc < nChunks; kc += 2) {
+        iter(kc, rg);
+        if (kc + 1 < nChunks) iter(kc + 1, rg2);
+      }
+    } else {
     fetchChunk(0);
     if (a.mode != 2) loadPos(0);
     if (nChunks > 1) fetchChunk(1);
-    long long sCp = 0, sEB = 0, sEC = 0, sT0 = (DBG ? clock64() : 0ll);
     for (int kc = 0; kc < nChunks; kc++) {
       const int buf = kc % a.nPB;
       long long c0 = (DBG ? clock64() : 0ll);
-      if (kc + 1 < nChunks) asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk kc landed, kc+1 may be in flight
-      else CpAsyncWaitAll();
-      // (each stager arrives after its own copies have landed; the barrier completes when all 96 have)
-      sCp += (DBG ? clock64() : 0ll) - c0;
-      MbarArrive(fullC + kc % kCbBufs);                  // the decoders may start on chunk kc
+      if (!a.bulkC) {
+        if (kc + 1 < nChunks) asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk kc landed, kc+1 may be in flight
+        else CpAsyncWaitAll();
+        // (each stager arrives after its own copies have landed; the barrier completes when all 96 have)
+        sCp += (DBG ? clock64() : 0ll) - c0;
+        MbarArrive(fullC + kc % kCbBufs);                  // the decoders may start on chunk kc
+      }
       c0 = (DBG ? clock64() : 0ll);
       if (kc >= a.nPB) MbarWait(emptyB + buf, ((kc / a.nPB) - 1) & 1);   // planes last read by the MMAs of chunk kc-nPB
       sEB += (DBG ? clock64() : 0ll) - c0;
@@ -519,6 +645,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
         sEC += (DBG ? clock64() : 0ll) - c0;
         fetchChunk(kc + 2);
       }
+    }
     }
     if (DBG && a.dbg && st == 0) {
       atomicAdd(a.dbg + 8, static_cast<unsigned long long>((DBG ? clock64() : 0ll) - sT0));
@@ -615,6 +742,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
     const int grp = (WIDE && warp >= 8) ? 1 : 0;    // WIDE: group 0 decodes the even stages, group 1 the odd ones
     const bool pre = BF && a.cbPre != 0;
     int t = 0, dslot = 0, dround = 0;
+    long long dP1 = 0, dP2 = 0, dP3 = 0, dP4 = 0, dP3s = 0;   // DBG: index loads / codeword loads / split + tcgen05.st issue / wait::st
     long long dFC = 0, dEA = 0, dT0 = (DBG ? clock64() : 0ll);
     for (int kc = 0; kc < nChunks; kc++) {
       const int cbuf = kc % kCbBufs;
@@ -626,6 +754,16 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
       const float* cbf = reinterpret_cast<const float*>(cb);
       const int e0 = a.chunkFirst[a.mode == 1 ? kcBase + kc : 0];
       const int ne = a.mode == 2 ? min(a.chunkCount[0], kTotal - kc * a.chunkCount[0]) : a.chunkCount[a.mode == 1 ? kcBase + kc : 0];
+      // idxT: every tap index of this channel for the chunk's two halves in registers (one or two 128-bit loads each): the
+      // per-k-step chain loses two dependent shared-memory round trips (table entry, index byte) -- under the load of the
+      // MMAs' operand fetch a round trip costs ~450 clk (role counters, profiles/README.md)
+      uint4 iA0 = make_uint4(0, 0, 0, 0), iA1 = iA0, iB0 = iA0, iB1 = iA0;
+      if (a.idxT) {
+        const uint4* ip = reinterpret_cast<const uint4*>(ids + cbuf * a.idRows * 128);
+        const int W = a.tapsPad >> 4;
+        iA0 = ip[cc * W]; iB0 = ip[(128 + cc) * W];
+        if (W > 1) { iA1 = ip[cc * W + 1]; iB1 = ip[(128 + cc) * W + 1]; }
+      }
       for (int s0 = 0; s0 < ne; s0 += GT, t++) {
         const int slot = dslot, round = dround;           // = t % NSLOT, t / NSLOT (kept incrementally: no divisions)
         if (++dslot == NSLOT) { dslot = 0; dround++; }
@@ -640,7 +778,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
         if (a.d == 1) {
           for (int i = 0; i < n; i++) {
             // scalar codewords: every feature is its own subspace (rows / slots idx0 .. idx0+3 and idx1 .. idx1+3)
-            const KStep ks = tabS[e0 + s0 + i];
+            const KStep ks = a.tab[e0 + s0 + i];
             const uint8_t* r0 = idb + ks.idx0 * 128;
             const uint8_t* r1 = idb + ks.idx1 * 128;
             const float* c0p = cbf + ks.cb0 * K;
@@ -657,19 +795,27 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
           // the stage's k-steps are independent: table entries, index bytes and codeword pieces of all of them are in
           // flight together (one decoder warp per SM sub-partition: latency, not bandwidth, paces this role)
           int i0x[MG], i1x[MG];
+          long long p0 = (DBG ? clock64() : 0ll);
 #pragma unroll
           for (int i = 0; i < MG; i++) {
             if (i < n) {
-              const KStep ks = tabS[e0 + s0 + i];
-              i0x[i] = ks.cb0 * K + (idb[ks.idx0 * 128] >> a.kshift);
-              i1x[i] = ks.cb1 * K + (idb[ks.idx1 * 128] >> a.kshift);
+              if (a.idxT) {      // mode 0: k-step = tap s0 + i, codebook slots 0 / 1
+                i0x[i] = ByteOf32(iA0, iA1, s0 + i);
+                i1x[i] = K + ByteOf32(iB0, iB1, s0 + i);
+              } else {
+                const KStep ks = a.tab[e0 + s0 + i];
+                i0x[i] = ks.cb0 * K + (idb[ks.idx0 * 128] >> a.kshift);
+                i1x[i] = ks.cb1 * K + (idb[ks.idx1 * 128] >> a.kshift);
+              }
             }
           }
+          if (DBG) { asm volatile("" :: "r"(i0x[0]), "r"(i1x[0]) : "memory"); dP1 += clock64() - p0; p0 = clock64(); }
           float4 w0[MG], w1[MG];
 #pragma unroll
           for (int i = 0; i < MG; i++) {
             if (i < n) { w0[i] = cb[i0x[i]]; w1[i] = cb[i1x[i]]; }
           }
+          if (DBG) { asm volatile("" :: "f"(w0[0].x), "f"(w1[0].x) : "memory"); dP2 += clock64() - p0; dP3s = clock64(); }
 #pragma unroll
           for (int i = 0; i < MG; i++) {
             if (i < n) {
@@ -679,7 +825,9 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
             }
           }
         }
+        if (DBG) { dP3 += clock64() - dP3s; dP3s = clock64(); }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (DBG) { dP4 += clock64() - dP3s; }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         MbarArrive(fullA + slot);
       }
@@ -689,6 +837,10 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
       atomicAdd(a.dbg + 12, static_cast<unsigned long long>((DBG ? clock64() : 0ll) - dT0));
       atomicAdd(a.dbg + 13, static_cast<unsigned long long>(dFC));
       atomicAdd(a.dbg + 14, static_cast<unsigned long long>(dEA));
+      atomicAdd(a.dbg + 4, static_cast<unsigned long long>(dP1));
+      atomicAdd(a.dbg + 6, static_cast<unsigned long long>(dP2));
+      atomicAdd(a.dbg + 7, static_cast<unsigned long long>(dP3));
+      atomicAdd(a.dbg + 15, static_cast<unsigned long long>(dP4));
     }
   }
 
@@ -866,6 +1018,9 @@ static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<dou
       ga.bf = L->opt_tc_bf ? 1 : 0;
       ga.planeRows = ga.bf ? ga.NPOS : ga.planeF4;   // (bf16x2: lbo = NPOS rows is the x1 -> x2 plane distance as well)
       ga.cbSlots = 2; ga.idRows = 2 * taps;
+      ga.tapsPad = RoundUp(taps, 16);
+      ga.idxT = (ga.tapsPad <= 32 && L->d_asmt_t) ? 1 : 0;
+      if (ga.idxT) ga.idRows = 2 * ga.tapsPad;      // [half][128 channels][tapsPad] bytes = 2 * tapsPad rows of 128
       ga.nChunks = CeilDiv(Cg, 8);
       ga.ntab = taps;
       ga.chunkFirst[0] = 0; ga.chunkCount[0] = taps;
@@ -955,13 +1110,13 @@ static int SetSmemLimitOnce(qcnn_ctx* ctx) {
 }
 
 // bf16x2 form of the codebook, made once per layer: every aligned 4-float piece becomes {w1 (4 x bf16), w2 (4 x bf16)},
-// same indexing and size as the fp32 codebook
+// stored [S][d/4][K] so that the K pieces a chunk stages are one contiguous run (bulk-copyable)
 int BuildCtrdBf(qcnn_layer* L) {
   if (L->d % 4 != 0 || L->d_ctrd_bf) return 0;
   const size_t n = static_cast<size_t>(L->S) * L->K * L->d / 4;
   QCNN_CUDA(cudaMalloc(&L->d_ctrd_bf, n * sizeof(uint4)));
   split_codebook_kernel<<<static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 1024)), 256>>>(
-      reinterpret_cast<const float4*>(L->d_ctrd), reinterpret_cast<uint4*>(L->d_ctrd_bf), n);
+      reinterpret_cast<const float4*>(L->d_ctrd), reinterpret_cast<uint4*>(L->d_ctrd_bf), L->S, L->K, L->d / 4);
   QCNN_CUDA(cudaGetLastError());
   QCNN_CUDA(cudaDeviceSynchronize());
   return 0;
@@ -971,6 +1126,8 @@ int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, floa
   GemmArgs a = p.g;
   a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
   if (a.bf && L->d_ctrd_bf) { a.ctrd = reinterpret_cast<const float*>(L->d_ctrd_bf); a.cbPre = 1; }
+  a.asmtT = L->d_asmt_t;
+  a.bulkC = (a.mode == 0 && a.idxT && a.cbPre) ? 1 : 0;
   a.N = N; a.relu = a.nsplit > 1 ? 0 : relu;
   if (a.nsplit < 1) a.nsplit = 1;
   a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;
@@ -1020,8 +1177,9 @@ int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, floa
     const double n = h[5] ? static_cast<double>(h[5]) : 1.0;
     fprintf(stderr, "[pq_gemm dbg] ctas=%llu NT=%d GT=%d chunks=%d ksteps=%d | per CTA: issue-loop %.0f clk (wait planes %.0f, wait weights %.0f), "
             "drain %.0f | stager loop %.0f (wait copies %.0f, wait planes free %.0f, wait cb free %.0f) | decoder loop %.0f (wait cb %.0f, "
-            "wait ring %.0f)\n", h[5], a.NT, a.GT, a.nChunks, a.chunkCount[0], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[8] / n, h[9] / n,
-            h[10] / n, h[11] / n, h[12] / n, h[13] / n, h[14] / n);
+            "wait ring %.0f; index loads %.0f, codeword loads %.0f, split + tcgen05.st %.0f, wait::st %.0f)\n", h[5], a.NT, a.GT, a.nChunks,
+            a.chunkCount[0], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[8] / n, h[9] / n,
+            h[10] / n, h[11] / n, h[12] / n, h[13] / n, h[14] / n, h[4] / n, h[6] / n, h[7] / n, h[15] / n);
     cudaFree(a.dbg);
   }
   if (a.nsplit > 1)

@@ -156,9 +156,19 @@ int qcnn_conv_layer_create(qcnn_ctx* ctx, int Cin, int Hin, int Win, int Cout, i
           dev[((static_cast<size_t>(g) * S + s) * taps + t) * KgPad + c] =
               asmt_h[((static_cast<size_t>(g) * Kg + c) * taps + t) * S + s];
   L->asmt_bytes = dev.size();
+  // channel-major copy for the tensor-core GEMM's decoders: [grp][S][KgPad][tapsPad]
+  const int tapsPad = RoundUp(taps, 16);
+  std::vector<uint8_t> devT(static_cast<size_t>(grp) * S * KgPad * tapsPad, 0);
+  for (int g = 0; g < grp; g++)
+    for (int s = 0; s < S; s++)
+      for (int c = 0; c < Kg; c++)
+        for (int t = 0; t < taps; t++)
+          devT[((static_cast<size_t>(g) * S + s) * KgPad + c) * tapsPad + t] = dev[((static_cast<size_t>(g) * S + s) * taps + t) * KgPad + c];
   int rc = 0;
   do {
     if ((rc = (cudaMalloc(&L->d_asmt, dev.size()) != cudaSuccess))) break;
+    if ((rc = (cudaMalloc(&L->d_asmt_t, devT.size()) != cudaSuccess))) break;
+    if ((rc = (cudaMemcpy(L->d_asmt_t, devT.data(), devT.size(), cudaMemcpyHostToDevice) != cudaSuccess))) break;
     if ((rc = (cudaMalloc(&L->d_ctrd, sizeof(float) * S * K * d) != cudaSuccess))) break;
     if ((rc = (cudaMalloc(&L->d_bias, sizeof(float) * Cout) != cudaSuccess))) break;
     if ((rc = (cudaMemcpy(L->d_asmt, dev.data(), dev.size(), cudaMemcpyHostToDevice) != cudaSuccess))) break;
@@ -290,6 +300,7 @@ void qcnn_layer_destroy(qcnn_layer* L) {
   if (!L) return;
   DeviceGuard guard(L->ctx->device);
   if (L->d_asmt) cudaFree(L->d_asmt);
+  if (L->d_asmt_t) cudaFree(L->d_asmt_t);
   if (L->d_ctrd) cudaFree(L->d_ctrd);
   if (L->d_bias) cudaFree(L->d_bias);
   if (L->d_partial) cudaFree(L->d_partial);

@@ -136,6 +136,9 @@ struct GemmArgs {
   int wide;                   // 1: the twelve-warp instantiation (second decoder warp group)
   int bf;                     // 1: bf16x2 operands (x = x1 + x2, w = w1 + w2 as bf16 pieces; TWO kind::f16 MMAs of K = 16 per
                               //    k-step: [w1|w1].[x1|x2] + [w2|w2].[x1|x2]) instead of 3xTF32 (three kind::tf32 MMAs of K = 8)
+  const uint8_t* asmtT;       // qcnn_layer::d_asmt_t (mode 0 with idxT)
+  int idxT, tapsPad;          // 1: the chunk's indices are staged channel-major ([half][128 channels][tapsPad bytes])
+  int bulkC;                  // mode 0 with idxT and cbPre: codebook slices + index blocks arrive by four cp.async.bulk per chunk
   int cbPre;                  // 1: `ctrd` is the pre-split codebook (qcnn_layer::d_ctrd_bf): the decoders convert nothing
   int planeRows;              // 16-byte rows per staged plane (3xTF32: planeF4; bf16x2: positions x k-step groups)
   int NPOS;                   // staged positions per plane (NT + halo)
@@ -173,6 +176,8 @@ struct qcnn_layer {
   // device parameters
   float* d_ctrd;
   uint8_t* d_asmt;
+  uint8_t* d_asmt_t;      // conv layers: the same indices as [grp][S][KgPad][tapsPad] (tapsPad = taps rounded up to 16): a decoder thread
+                          // (= channel) reads all taps of a chunk with one or two 128-bit loads (pq_gemm_tc.cu, mode 0)
   float* d_bias;
   size_t asmt_bytes;
   int kshift;           // FC: stored assignment = idx << kshift
@@ -187,7 +192,7 @@ struct qcnn_layer {
   size_t partial_bytes;
   float* d_flat;         // tensor-core FC path: source pre-split into hi/lo plane images (fc_prep_kernel)
   size_t flat_bytes;
-  void* d_ctrd_bf;        // codebook pre-split into bf16 pieces (pq_gemm_tc.cu, bf16x2 operands): per 4-float piece {w1 (4 x bf16), w2 (4 x bf16)}
+  void* d_ctrd_bf;        // codebook pre-split into bf16 pieces (pq_gemm_tc.cu, bf16x2 operands): [S][d/4 pieces][K] x {w1 (4 x bf16), w2 (4 x bf16)}: a (subspace, piece) slice is contiguous
   float* d_cpart;        // chain kernel (fc_chain.cu): per-CTA partial sums [sm_count][DoutPad], words double as ready flags
   size_t cpart_bytes;
   // tuning overrides (0 = automatic)

@@ -1442,7 +1442,7 @@ int DescribeConv(qcnn_layer* L, int N, char* buf, size_t cap) {
     int ksteps = 0;
     for (int c = 0; c < p.g.nChunks; c++) ksteps += p.g.chunkCount[p.g.mode == 1 ? c : 0];
     snprintf(buf, cap, "pq_gemm_tc(tcgen05, weights decoded into TMEM%s) mode=%d NT=%d GT=%d slots=%d smem=%zuB grid=%d NPOS=%d "
-             "chunks=%d ksteps=%d nsplit=%d", p.g.bf ? (p.g.lite ? ", bf16x2, 2 CTAs/SM" : (p.g.wide ? ", bf16x2, 8 decoder warps" : ", bf16x2"))
+             "chunks=%d ksteps=%d nsplit=%d", p.g.bf ? (p.g.lite ? ", bf16x2, 2 CTAs/SM" : (p.g.wide ? ", bf16x2, 8 decoder warps" : (p.g.xl ? ", bf16x2, 16 warps" : ", bf16x2")))
                     : (p.g.lite ? ", 2 CTAs/SM" : (p.g.wide ? ", 8 decoder warps" : "")), p.g.mode, p.g.NT, p.g.GT, p.g.NSLOT, p.smem,
              CeilDiv(N * p.g.IB, p.g.NT) * L->grp * p.g.nct * std::max(1, p.g.nsplit), p.g.NPOS, p.g.nChunks,
              ksteps / std::max(1, p.g.nsplit), std::max(1, p.g.nsplit));

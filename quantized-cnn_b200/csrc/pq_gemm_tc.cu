@@ -211,11 +211,15 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
 // WIDE: a SECOND group of four decoder warps (warps 8-11; 384 threads): the two groups take the stages alternately.  The
 // decoders -- one warp per SM sub-partition, a chain of dependent shared-memory reads, the split and a tcgen05.st per
 // k-step -- are what paces the kernel (~400 clk per k-step against 384 clk of 3xTF32 MMAs or 256 clk of bf16x2 MMAs).
-template <bool DBG, bool LITE, bool BF, bool WIDE>
-__global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_tc_kernel(const GemmArgs a) {
-  constexpr int NTHR = WIDE ? 384 : kThreads;
-  constexpr int RP = (LITE || WIDE) ? kRegPosLite : kRegPos;
-  constexpr int MG = LITE ? kMaxGTLite : (WIDE ? 5 : kMaxGT);
+// XL: sixteen warps (512 threads, <= 128 registers): two decoder groups AND seven stager warps (5-7, 12-15) -- conv1's tiles
+// (16-18 k-steps per phase row, four phase columns of 3-channel pixels to stage per row) need both to keep the MMAs fed.
+template <bool DBG, bool LITE, bool BF, bool WIDE, bool XL = false>
+__global__ void __launch_bounds__(XL ? 512 : (WIDE ? 384 : kThreads), LITE ? 2 : 1) pq_gemm_tc_kernel(const GemmArgs a) {
+  constexpr int NTHR = XL ? 512 : (WIDE ? 384 : kThreads);
+  constexpr int NSTG = XL ? kStagers + 128 : kStagers;      // stager threads
+  constexpr bool TWOG = WIDE || XL;                          // two decoder groups (warps 0-3 and 8-11)
+  constexpr int RP = XL ? 7 : ((LITE || WIDE) ? kRegPosLite : kRegPos);
+  constexpr int MG = (LITE || XL) ? kMaxGTLite : (WIDE ? 5 : kMaxGT);
   constexpr uint32_t kTmemCols = LITE ? 256u : 512u;
   extern __shared__ __align__(128) unsigned char smem[];
   const SmemMap sm = MapSmem(a);
@@ -310,8 +314,8 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
   }
   if (tid == 0) {
     for (int i = 0; i < kMaxSlots; i++) { MbarInit(fullA + i, kDecoders); MbarInit(emptyA + i, 1); }
-    for (int i = 0; i < 4; i++) { MbarInit(fullB + i, kStagers); MbarInit(emptyB + i, 1); }
-    for (int i = 0; i < kCbBufs; i++) { MbarInit(fullC + i, a.bulkC ? 1 : kStagers); MbarInit(emptyC + i, WIDE ? 2 * kDecoders : kDecoders); }
+    for (int i = 0; i < 4; i++) { MbarInit(fullB + i, NSTG); MbarInit(emptyB + i, 1); }
+    for (int i = 0; i < kCbBufs; i++) { MbarInit(fullC + i, a.bulkC ? 1 : NSTG); MbarInit(emptyC + i, TWOG ? 2 * kDecoders : kDecoders); }
     MbarInit(doneBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -322,9 +326,10 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
   const uint32_t tmemA = tmemD + static_cast<uint32_t>(a.aOff);   // A ring: columns [aOff, aOff + NSLOT*GT*16)
 
   const int warpU = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform role selector
-  if (warpU >= 5 && warpU < 8) {
+  if ((warpU >= 5 && warpU < 8) || (XL && warpU >= 12)) {
     // =========================== stagers ===========================
-    const int st = tid - kStager0;
+    const int st = warpU < 8 ? tid - kStager0 : kStagers + tid - 384;
+    const int sw = st >> 5;                      // stager warp 0 .. NSTG/32 - 1
     // 4-float piece j0/4 of codeword k of subspace s: fp32 codebook [S][K][d] or the pre-split one [S][d/4][K][4 words]
     auto piece = [&](int s, int j0, int k) -> const float* {
       return a.cbPre ? a.ctrd + ((static_cast<size_t>(s) * (a.d >> 2) + (j0 >> 2)) * K + k) * 4
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
           }
           return;
         }
-        for (int k = st; k < K; k += kStagers) {
+        for (int k = st; k < K; k += NSTG) {
           CpAsync16(cdst + k, piece(sA, jA, k), okA);
           CpAsync16(cdst + K + k, piece(sB, jB, k), okB);
         }
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
           const uint8_t* tA = a.asmtT + (static_cast<size_t>(g * a.S + sA) * a.KgPad + ch0) * a.tapsPad;
           const uint8_t* tB = a.asmtT + (static_cast<size_t>(g * a.S + sB) * a.KgPad + ch0) * a.tapsPad;
           uint8_t* idst = ids + cbuf * a.idRows * 128;
-          for (int e = st; e < 2 * gran; e += kStagers) {
+          for (int e = st; e < 2 * gran; e += NSTG) {
             const bool hb = e >= gran;
             const int q = hb ? e - gran : e;
             CpAsync16(idst + (hb ? 128 * a.tapsPad : 0) + (q << 4), (hb ? tB : tA) + (static_cast<size_t>(q) << 4), true);
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
           const uint8_t* asA = a.asmt + static_cast<size_t>(g * a.S + sA) * taps * a.KgPad + ch0 + (lane << 4);
           const uint8_t* asB = a.asmt + static_cast<size_t>(g * a.S + sB) * taps * a.KgPad + ch0 + (lane << 4);
           uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
-          for (int row = warp - 5; row < 2 * taps; row += 3) {
+          for (int row = sw; row < 2 * taps; row += NSTG / 32) {
             const bool hb = row >= taps;
             const int tap = hb ? row - taps : row;
             CpAsync16(idst + row * 128, (hb ? asB : asA) + static_cast<size_t>(tap) * a.KgPad, true);
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
         // (positions travel through registers: loadPos / storePos)
         // codebook: slot 0 = the first 4 floats of every codeword of subspace 0, slot 1 = zeros (unpaired taps)
         float4* cdst = cbs + cbuf * a.cbSlots * K;
-        for (int k = st; k < K; k += kStagers) {
+        for (int k = st; k < K; k += NSTG) {
           CpAsync16(cdst + k, piece(0, 0, k), true);
           CpAsync16(cdst + K + k, a.ctrd, false);
         }
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
           const uint8_t* as0 = a.asmt + static_cast<size_t>(g * a.S) * a.ksz * a.ksz * a.KgPad + ch0 + (lane << 4);
           uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
           const int nrow = ((a.ksz - ph + a.stride - 1) / a.stride) * a.ksz;
-          for (int row = warp - 5; row < nrow; row += 3) {
+          for (int row = sw; row < nrow; row += NSTG / 32) {
             const int kh = ph + (row / a.ksz) * a.stride, kw = row % a.ksz;
             CpAsync16(idst + row * 128, as0 + static_cast<size_t>(kh * a.ksz + kw) * a.KgPad, true);
           }
@@ -424,16 +429,16 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
           // slot q = subspace f0 + q: its K scalar codewords; index row q
           const int kq = K >> 2;
           float4* cdst = cbs + cbuf * a.cbSlots * a.cbF4;
-          for (int e = st; e < 8 * ne * kq; e += kStagers) CpAsync16(cdst + e, a.ctrd + static_cast<size_t>(f0) * K + e * 4, true);
+          for (int e = st; e < 8 * ne * kq; e += NSTG) CpAsync16(cdst + e, a.ctrd + static_cast<size_t>(f0) * K + e * 4, true);
           if (lane < gran) {
             const uint8_t* as0 = a.asmt + static_cast<size_t>(f0) * a.KgPad + ch0 + (lane << 4);
             uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
-            for (int row = warp - 5; row < 8 * ne; row += 3) CpAsync16(idst + row * 128, as0 + static_cast<size_t>(row) * a.KgPad, true);
+            for (int row = sw; row < 8 * ne; row += NSTG / 32) CpAsync16(idst + row * 128, as0 + static_cast<size_t>(row) * a.KgPad, true);
           }
         } else {
           // slot q = features [f0 + 4q, +4): piece j0 of every codeword of subspace s; index row q = row s of the layer
           float4* cdst = cbs + cbuf * a.cbSlots * a.cbF4;
-          for (int e = st; e < 2 * ne * K; e += kStagers) {
+          for (int e = st; e < 2 * ne * K; e += NSTG) {
             const int q = e / K, k = e - q * K;
             const int f = f0 + 4 * q;
             const int s = f / a.d, j0 = f - s * a.d;
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
           }
           if (lane < gran) {
             uint8_t* idst = ids + cbuf * a.idRows * 128 + (lane << 4);
-            for (int row = warp - 5; row < 2 * ne; row += 3) {
+            for (int row = sw; row < 2 * ne; row += NSTG / 32) {
               const int s = (f0 + 4 * row) / a.d;
               CpAsync16(idst + row * 128, a.asmt + static_cast<size_t>(s) * a.KgPad + ch0 + (lane << 4), true);
             }
@@ -461,7 +466,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
     if (a.mode != 2) {
 #pragma unroll
       for (int i = 0; i < RP; i++) {
-        const int p = st + i * kStagers;
+        const int p = st + i * NSTG;
         poffR[i] = 0; prowR[i] = -(1 << 28);
         if (p < a.planeF4) {
           const int off = posoff[p];
@@ -511,13 +516,13 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
     // a whole chunk instead of being waited for in every iteration -- with one set the stagers, not the MMAs, paced these
     // layers (role counters: 3.8 k clk per chunk against 2.4 k clk of MMAs).
     constexpr int H = 6;
-    const bool dbl = WIDE && a.mode == 0 && a.planeF4 <= H * kStagers;
+    const bool dbl = WIDE && a.mode == 0 && a.planeF4 <= H * NSTG;
     if (WIDE && dbl) {
       float4 rg2[WIDE ? H : 1];
       int pdst[WIDE ? H : 1];           // bf16x2: byte offset of the element inside a plane (chunk-invariant)
 #pragma unroll
       for (int i = 0; i < H; i++) {
-        const int p = st + i * kStagers;
+        const int p = st + i * NSTG;
         const int grp = p >= a.NPOS ? 1 : 0;
         pdst[i] = (p - grp * a.NPOS) * 16 + grp * 8;
       }
@@ -549,7 +554,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
         float4* pLo = planes + (buf * 2 + 1) * a.planeRows;
 #pragma unroll
         for (int i = 0; i < H; i++) {
-          const int p = st + i * kStagers;
+          const int p = st + i * NSTG;
           if (p < a.planeF4) {
             if (BF) {
               uint2 p1, p2;
@@ -616,7 +621,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
       } else {
 #pragma unroll
         for (int i = 0; i < RP; i++) {
-          const int p = st + i * kStagers;
+          const int p = st + i * NSTG;
           if (p < a.planeF4) {
             if (BF) {
               uint2 p1, p2;
@@ -739,7 +744,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
     const int c = (warp & 3) * 32 + lane;           // channel row = TMEM lane (a warp reaches the lanes of its sub-partition)
     const int cc = min(c, CTv - 1);                 // rows beyond the valid channels decode a copy (never stored)
     const uint32_t laneBase = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const int grp = (WIDE && warp >= 8) ? 1 : 0;    // WIDE: group 0 decodes the even stages, group 1 the odd ones
+    const int grp = (TWOG && warp >= 8) ? 1 : 0;    // WIDE: group 0 decodes the even stages, group 1 the odd ones
     const bool pre = BF && a.cbPre != 0;
     int t = 0, dslot = 0, dround = 0;
     long long dP1 = 0, dP2 = 0, dP3 = 0, dP4 = 0, dP3s = 0;   // DBG: index loads / codeword loads / split + tcgen05.st issue / wait::st
@@ -767,7 +772,7 @@ __global__ void __launch_bounds__(WIDE ? 384 : kThreads, LITE ? 2 : 1) pq_gemm_t
       for (int s0 = 0; s0 < ne; s0 += GT, t++) {
         const int slot = dslot, round = dround;           // = t % NSLOT, t / NSLOT (kept incrementally: no divisions)
         if (++dslot == NSLOT) { dslot = 0; dround++; }
-        if (WIDE && (t & 1) != grp) continue;
+        if (TWOG && (t & 1) != grp) continue;
         if (round > 0) {
           c0 = (DBG ? clock64() : 0ll);
           MbarWait(emptyA + slot, (round - 1) & 1);
@@ -896,6 +901,7 @@ namespace qcnn {
 // Candidate tilings for batch N (cost in SM-cycles, comparable with PlanConv's model): 3 MMAs of NT/2 clk per k-step.
 void AddLitePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first);
 void AddWidePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first);
+void AddXlPqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first);
 static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands);
 void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPlan>>* cands) {
   const size_t first = cands->size();
@@ -903,6 +909,8 @@ void PlanPqGemm(const qcnn_layer* L, int N, std::vector<std::pair<double, ConvPl
   static const bool lite = !(getenv("QCNN_GEMM_LITE") && getenv("QCNN_GEMM_LITE")[0] == '0');
   static const bool wide = !(getenv("QCNN_GEMM_WIDE") && getenv("QCNN_GEMM_WIDE")[0] == '0');
   const size_t mid = cands->size();
+  static const bool xl = !(getenv("QCNN_GEMM_XL") && getenv("QCNN_GEMM_XL")[0] == '0');
+  if (xl) AddXlPqGemm(L, cands, first);
   if (wide) AddWidePqGemm(L, cands, first);
   if (lite) {
     const size_t end = cands->size();
@@ -1063,11 +1071,27 @@ void AddWidePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>
   for (size_t i = first; i < n; i++) {
     ConvPlan p = (*cands)[i].second;
     GemmArgs& ga = p.g;
-    if (p.kernel != 6 || ga.lite || ga.GT > 5 || ga.planeF4 > kRegPosLite * kStagers || ga.NSLOT < 2) continue;
+    if (p.kernel != 6 || ga.lite || ga.xl || ga.GT > 5 || ga.planeF4 > kRegPosLite * kStagers || ga.NSLOT < 2) continue;
     ga.wide = 1;
     p.threads = 384;
     p.J = ga.GT + 200;     // (candidate de-duplication key)
     cands->emplace_back((*cands)[i].first * 0.85, p);
+  }
+}
+
+// Sixteen-warp variants for mode 1 (conv1): tiles of 256 positions, stages of <= 4 k-steps, 224 stager threads
+void AddXlPqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>* cands, size_t first) {
+  (void)L;
+  const size_t n = cands->size();
+  for (size_t i = first; i < n; i++) {
+    ConvPlan p = (*cands)[i].second;
+    GemmArgs& ga = p.g;
+    if (p.kernel != 6 || ga.lite || ga.wide || ga.mode != 1 || !ga.bf || ga.GT > kMaxGTLite || ga.NSLOT < 2 ||
+        ga.planeF4 > 7 * (kStagers + 128)) continue;
+    ga.xl = 1;
+    p.threads = 512;
+    p.J = ga.GT + 300;     // (candidate de-duplication key)
+    cands->emplace_back((*cands)[i].first * 0.7, p);
   }
 }
 
@@ -1078,7 +1102,7 @@ void AddLitePqGemm(const qcnn_layer* L, std::vector<std::pair<double, ConvPlan>>
   for (size_t i = first; i < n; i++) {
     ConvPlan p = (*cands)[i].second;
     GemmArgs& ga = p.g;
-    if (p.kernel != 6 || ga.wide || ga.NT > 128 || ga.GT > kMaxGTLite || ga.planeF4 > kRegPosLite * kStagers || p.smem > perCtaSmem) continue;
+    if (p.kernel != 6 || ga.wide || ga.xl || ga.NT > 128 || ga.GT > kMaxGTLite || ga.planeF4 > kRegPosLite * kStagers || p.smem > perCtaSmem) continue;
     const int ring = ga.NSLOT * ga.GT * 16;
     ga.NSLOT = std::min(ga.NSLOT, (256 - ga.NT) / (ga.GT * 16));
     if (ga.NSLOT < 2) continue;
@@ -1101,6 +1125,7 @@ static int SetSmemLimitOnce(qcnn_ctx* ctx) {
   QCNN_SMEM_ATTR(false, false, false, false); QCNN_SMEM_ATTR(true, false, false, false); QCNN_SMEM_ATTR(false, true, false, false);
   QCNN_SMEM_ATTR(false, false, true, false);  QCNN_SMEM_ATTR(true, false, true, false);  QCNN_SMEM_ATTR(false, true, true, false);
   QCNN_SMEM_ATTR(false, false, false, true);  QCNN_SMEM_ATTR(false, false, true, true);  QCNN_SMEM_ATTR(true, false, true, true);
+  QCNN_SMEM_ATTR(false, false, true, false, true);  QCNN_SMEM_ATTR(true, false, true, false, true);
 #undef QCNN_SMEM_ATTR
   // the lite kernels' CTAs must really pair up: ask for the largest shared-memory carve-out
   QCNN_CUDA(cudaFuncSetAttribute(pq_gemm_tc_kernel<false, true, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1157,7 +1182,10 @@ int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, floa
     QCNN_CUDA(cudaMemsetAsync(a.dbg, 0, 128, st));
   }
   const unsigned nb = static_cast<unsigned>(blocks);
-  if (a.wide) {
+  if (a.xl) {
+    if (dbg) pq_gemm_tc_kernel<true, false, true, false, true><<<nb, 512, p.smem, st>>>(a);
+    else pq_gemm_tc_kernel<false, false, true, false, true><<<nb, 512, p.smem, st>>>(a);
+  } else if (a.wide) {
     if (a.bf) { if (dbg) pq_gemm_tc_kernel<true, false, true, true><<<nb, 384, p.smem, st>>>(a); else pq_gemm_tc_kernel<false, false, true, true><<<nb, 384, p.smem, st>>>(a); }
     else pq_gemm_tc_kernel<false, false, false, true><<<nb, 384, p.smem, st>>>(a);
   } else if (a.bf) {

@@ -134,6 +134,7 @@ struct GemmArgs {
   int corr;                   // 1: the 3xTF32 cross terms have their own accumulator at column NT (added in the epilogue)
   int lite;                   // 1: the two-CTAs-per-SM instantiation (256 TMEM columns, short register windows)
   int wide;                   // 1: the twelve-warp instantiation (second decoder warp group)
+  int xl;                     // 1: the sixteen-warp instantiation (second decoder group + 224 stager threads; mode 1)
   int bf;                     // 1: bf16x2 operands (x = x1 + x2, w = w1 + w2 as bf16 pieces; TWO kind::f16 MMAs of K = 16 per
                               //    k-step: [w1|w1].[x1|x2] + [w2|w2].[x1|x2]) instead of 3xTF32 (three kind::tf32 MMAs of K = 8)
   const uint8_t* asmtT;       // qcnn_layer::d_asmt_t (mode 0 with idxT)

@@ -186,6 +186,15 @@ __device__ __forceinline__ int ByteOf32(const uint4 lo, const uint4 hi, int t) {
   return static_cast<int>((v >> ((t & 3) * 8)) & 0xFFu);
 }
 
+// byte t (< 48) of the 48 bytes {q0, q1, q2}
+__device__ __forceinline__ int ByteOf48(const uint4 q0, const uint4 q1, const uint4 q2, int t) {
+  const int hi = t >> 4;
+  const uint4 q = hi == 0 ? q0 : (hi == 1 ? q1 : q2);
+  const uint32_t xy = (t & 4) ? q.y : q.x, zw = (t & 4) ? q.w : q.z;
+  const uint32_t v = (t & 8) ? zw : xy;
+  return static_cast<int>((v >> ((t & 3) * 8)) & 0xFFu);
+}
+
 struct SmemMap {  // byte offsets inside the dynamic shared memory
   int planes, cbs, ids, tab, posoff, posrow, posdst, outoff, bias, bars, tmem, total;
 };
@@ -307,6 +316,8 @@ __global__ void __launch_bounds__(XL ? 512 : (WIDE ? 384 : kThreads), LITE ? 2 :
     }
     outoff[p] = off;
   }
+  if (a.mode == 1 && a.bulkC)      // slot 1 (unpaired taps) stays zero; slot 0 arrives by bulk copy
+    for (int e = tid; e < kCbBufs * K; e += NTHR) cbs[(e / K) * a.cbSlots * K + K + (e % K)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   for (int c = tid; c < 128; c += NTHR) biasS[c] = (c < CTv && split == 0) ? __ldg(a.bias + g * a.Kg + ch0 + c) : 0.0f;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmemBase)), "r"(kTmemCols) : "memory");
@@ -403,6 +414,19 @@ __global__ void __launch_bounds__(XL ? 512 : (WIDE ? 384 : kThreads), LITE ? 2 :
         // (positions travel through registers: loadPos / storePos)
         // codebook: slot 0 = the first 4 floats of every codeword of subspace 0, slot 1 = zeros (unpaired taps)
         float4* cdst = cbs + cbuf * a.cbSlots * K;
+        if (a.bulkC) {
+          if (st == 0) {
+            const uint32_t cbBytes = static_cast<uint32_t>(K) * 16u, idBytes = static_cast<uint32_t>(CTv * a.tapsPad);
+            const uint32_t bar = SmemU32(fullC + cbuf);
+            const uint8_t* tA = a.asmtT + (static_cast<size_t>(g * a.stride + ph) * a.KgPad + ch0) * a.tapsPad;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cbBytes + idBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(SmemU32(cdst)), "l"(piece(0, 0, 0)), "r"(cbBytes), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(SmemU32(ids + cbuf * a.idRows * 128)), "l"(tA), "r"(idBytes), "r"(bar) : "memory");
+          }
+          return;
+        }
         for (int k = st; k < K; k += NSTG) {
           CpAsync16(cdst + k, piece(0, 0, k), true);
           CpAsync16(cdst + K + k, a.ctrd, false);
@@ -766,8 +790,14 @@ __global__ void __launch_bounds__(XL ? 512 : (WIDE ? 384 : kThreads), LITE ? 2 :
       if (a.idxT) {
         const uint4* ip = reinterpret_cast<const uint4*>(ids + cbuf * a.idRows * 128);
         const int W = a.tapsPad >> 4;
-        iA0 = ip[cc * W]; iB0 = ip[(128 + cc) * W];
-        if (W > 1) { iA1 = ip[cc * W + 1]; iB1 = ip[(128 + cc) * W + 1]; }
+        iA0 = ip[cc * W];
+        if (a.mode == 1) {          // one block of <= 48 rows: iA0, iA1, iB0
+          if (W > 1) iA1 = ip[cc * W + 1];
+          if (W > 2) iB0 = ip[cc * W + 2];
+        } else {
+          iB0 = ip[(128 + cc) * W];
+          if (W > 1) { iA1 = ip[cc * W + 1]; iB1 = ip[(128 + cc) * W + 1]; }
+        }
       }
       for (int s0 = 0; s0 < ne; s0 += GT, t++) {
         const int slot = dslot, round = dround;           // = t % NSLOT, t / NSLOT (kept incrementally: no divisions)
@@ -804,7 +834,11 @@ __global__ void __launch_bounds__(XL ? 512 : (WIDE ? 384 : kThreads), LITE ? 2 :
 #pragma unroll
           for (int i = 0; i < MG; i++) {
             if (i < n) {
-              if (a.idxT) {      // mode 0: k-step = tap s0 + i, codebook slots 0 / 1
+              if (a.idxT && a.mode == 1) {   // rows and codebook slots from the k-step table (constant bank), bytes from registers
+                const KStep ks = a.tab[e0 + s0 + i];
+                i0x[i] = ks.cb0 * K + ByteOf48(iA0, iA1, iB0, ks.idx0);
+                i1x[i] = ks.cb1 * K + ByteOf48(iA0, iA1, iB0, ks.idx1);
+              } else if (a.idxT) {           // mode 0: k-step = tap s0 + i, codebook slots 0 / 1
                 i0x[i] = ByteOf32(iA0, iA1, s0 + i);
                 i1x[i] = K + ByteOf32(iB0, iB1, s0 + i);
               } else {
@@ -951,6 +985,9 @@ static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<dou
         if (ga.bf && (st & 1)) continue;       // bf16x2 rows hold a PAIR of phase columns
         ga.planeRows = ga.bf ? (st / 2) * ga.NPOS : ga.planeF4;
         ga.cbSlots = 2; ga.idRows = rowsPer * L->ksz;
+        ga.tapsPad = RoundUp(rowsPer * L->ksz, 16);
+        ga.idxT = (ga.tapsPad <= 48 && L->d_asmt_t && L->asmt_t_mode == 1) ? 1 : 0;
+        if (ga.idxT) ga.idRows = ga.tapsPad;       // [128 channels][tapsPad] bytes
         ga.nChunks = st;
         ga.K = L->K; ga.cbF4 = L->K; ga.nPB = 2;
         // bf16x2 planes are half the size: keep EVERY phase row of the tile resident (no plane reuse), so that the stagers
@@ -1027,7 +1064,7 @@ static void PlanPqGemmFull(const qcnn_layer* L, int N, std::vector<std::pair<dou
       ga.planeRows = ga.bf ? ga.NPOS : ga.planeF4;   // (bf16x2: lbo = NPOS rows is the x1 -> x2 plane distance as well)
       ga.cbSlots = 2; ga.idRows = 2 * taps;
       ga.tapsPad = RoundUp(taps, 16);
-      ga.idxT = (ga.tapsPad <= 32 && L->d_asmt_t) ? 1 : 0;
+      ga.idxT = (ga.tapsPad <= 32 && L->d_asmt_t && L->asmt_t_mode == 0) ? 1 : 0;
       if (ga.idxT) ga.idRows = 2 * ga.tapsPad;      // [half][128 channels][tapsPad] bytes = 2 * tapsPad rows of 128
       ga.nChunks = CeilDiv(Cg, 8);
       ga.ntab = taps;
@@ -1152,7 +1189,8 @@ int LaunchPqGemm(qcnn_layer* L, const ConvPlan& p, const float* src, int N, floa
   a.src = src; a.dst = dst; a.ctrd = L->d_ctrd; a.asmt = L->d_asmt; a.bias = L->d_bias;
   if (a.bf && L->d_ctrd_bf) { a.ctrd = reinterpret_cast<const float*>(L->d_ctrd_bf); a.cbPre = 1; }
   a.asmtT = L->d_asmt_t;
-  a.bulkC = (a.mode == 0 && a.idxT && a.cbPre) ? 1 : 0;
+  a.bulkC = (a.mode != 2 && a.idxT && a.cbPre) ? 1 : 0;
+  if (a.mode == 1 && !a.bulkC) a.idxT = 0;   // (3xTF32 operands: index rows by cp.async in tap-major order; the planned buffer is large enough)
   a.N = N; a.relu = a.nsplit > 1 ? 0 : relu;
   if (a.nsplit < 1) a.nsplit = 1;
   a.Hi = L->Hin; a.Wi = L->Win; a.Cin = L->Cin; a.Ho = L->Ho; a.Wo = L->Wo; a.Cout = L->Cout;

@@ -158,12 +158,27 @@ int qcnn_conv_layer_create(qcnn_ctx* ctx, int Cin, int Hin, int Win, int Cout, i
   L->asmt_bytes = dev.size();
   // channel-major copy for the tensor-core GEMM's decoders: [grp][S][KgPad][tapsPad]
   const int tapsPad = RoundUp(taps, 16);
-  std::vector<uint8_t> devT(static_cast<size_t>(grp) * S * KgPad * tapsPad, 0);
-  for (int g = 0; g < grp; g++)
-    for (int s = 0; s < S; s++)
-      for (int c = 0; c < Kg; c++)
-        for (int t = 0; t < taps; t++)
-          devT[((static_cast<size_t>(g) * S + s) * KgPad + c) * tapsPad + t] = dev[((static_cast<size_t>(g) * S + s) * taps + t) * KgPad + c];
+  std::vector<uint8_t> devT;
+  if (stride > 1 && S == 1) {
+    // strided layers (conv1): one block per phase row ph, row r <-> tap (kh = ph + (r / ksz) * stride, kw = r % ksz)
+    const int rowsPad = RoundUp(((ksz + stride - 1) / stride) * ksz, 16);
+    L->asmt_t_mode = 1;
+    devT.assign(static_cast<size_t>(grp) * stride * KgPad * rowsPad, 0);
+    for (int g = 0; g < grp; g++)
+      for (int ph = 0; ph < stride; ph++)
+        for (int c = 0; c < Kg; c++)
+          for (int kh = ph, r0 = 0; kh < ksz; kh += stride, r0 += ksz)
+            for (int kw = 0; kw < ksz; kw++)
+              devT[((static_cast<size_t>(g) * stride + ph) * KgPad + c) * rowsPad + r0 + kw] =
+                  dev[(static_cast<size_t>(g) * taps + kh * ksz + kw) * KgPad + c];
+  } else {
+    devT.assign(static_cast<size_t>(grp) * S * KgPad * tapsPad, 0);
+    for (int g = 0; g < grp; g++)
+      for (int s = 0; s < S; s++)
+        for (int c = 0; c < Kg; c++)
+          for (int t = 0; t < taps; t++)
+            devT[((static_cast<size_t>(g) * S + s) * KgPad + c) * tapsPad + t] = dev[((static_cast<size_t>(g) * S + s) * taps + t) * KgPad + c];
+  }
   int rc = 0;
   do {
     if ((rc = (cudaMalloc(&L->d_asmt, dev.size()) != cudaSuccess))) break;

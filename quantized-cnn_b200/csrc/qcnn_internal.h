@@ -177,6 +177,7 @@ struct qcnn_layer {
   // device parameters
   float* d_ctrd;
   uint8_t* d_asmt;
+  int asmt_t_mode;        // layout of d_asmt_t: 0 = [grp][S][KgPad][tapsPad] (stride 1), 1 = [grp][stride phase rows][KgPad][rowsPad] (strided, S = 1)
   uint8_t* d_asmt_t;      // conv layers: the same indices as [grp][S][KgPad][tapsPad] (tapsPad = taps rounded up to 16): a decoder thread
                           // (= channel) reads all taps of a chunk with one or two 128-bit loads (pq_gemm_tc.cu, mode 0)
   float* d_bias;

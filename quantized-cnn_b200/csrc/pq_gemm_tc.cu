@@ -204,7 +204,7 @@ __host__ __device__ inline SmemMap MapSmem(const GemmArgs& a) {
   m.planes = o; o += a.nPB * 2 * a.planeRows * 16;      // [buf][hi,lo | x1,x2][planeRows] 16-byte rows
   m.cbs = o;    o += kCbBufs * a.cbSlots * a.cbF4 * 16; // [cbuf][slot][cbF4] codeword pieces (raw fp32)
   m.ids = o;    o += kCbBufs * a.idRows * 128;          // [cbuf][row][128 channels] assignment indices
-  m.tab = o;                                            // (the k-step table is read from the kernel parameters)
+  m.tab = o;    o += a.ntab * 16;                       // k-step table for the decoders that do not keep their indices in registers
   m.posoff = o; o += a.planeF4 * 4;                     // source element offset of every staged float4 (-1: zero)
   m.posrow = o; o += a.mode == 1 ? a.planeF4 * 4 : 0;   // mode 1: first input row of the position (phase row 0)
   m.posdst = o; o += (a.bf && a.mode != 2) ? a.planeF4 * 4 : 0;   // bf16x2: byte offset of every staged float4 inside a plane
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(XL ? 512 : (WIDE ? 384 : kThreads), LITE ? 2 :
   float4* planes = reinterpret_cast<float4*>(smem + sm.planes);
   float4* cbs = reinterpret_cast<float4*>(smem + sm.cbs);
   uint8_t* ids = smem + sm.ids;
+  KStep* tabS = reinterpret_cast<KStep*>(smem + sm.tab);   // (FC tiles: shared memory is lightly loaded there and an LDS beats an indexed LDC)
   int* posoff = reinterpret_cast<int*>(smem + sm.posoff);
   int* posrow = reinterpret_cast<int*>(smem + sm.posrow);
   int* posdst = reinterpret_cast<int*>(smem + sm.posdst);
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(XL ? 512 : (WIDE ? 384 : kThreads), LITE ? 2 :
     dstBase = a.partial + (static_cast<size_t>(split) * a.N + i0) * a.dstImg + g * a.Kg + ch0;
 
   // ---- set-up (all threads) ----
+  for (int e = tid; e < a.ntab; e += NTHR) tabS[e] = a.tab[e];
   for (int p = tid; p < a.planeF4; p += NTHR) {
     int off = -1;
     if (a.mode == 0) {
@@ -813,7 +815,7 @@ __global__ void __launch_bounds__(XL ? 512 : (WIDE ? 384 : kThreads), LITE ? 2 :
         if (a.d == 1) {
           for (int i = 0; i < n; i++) {
             // scalar codewords: every feature is its own subspace (rows / slots idx0 .. idx0+3 and idx1 .. idx1+3)
-            const KStep ks = a.tab[e0 + s0 + i];
+            const KStep ks = tabS[e0 + s0 + i];
             const uint8_t* r0 = idb + ks.idx0 * 128;
             const uint8_t* r1 = idb + ks.idx1 * 128;
             const float* c0p = cbf + ks.cb0 * K;
@@ -831,20 +833,34 @@ __global__ void __launch_bounds__(XL ? 512 : (WIDE ? 384 : kThreads), LITE ? 2 :
           // flight together (one decoder warp per SM sub-partition: latency, not bandwidth, paces this role)
           int i0x[MG], i1x[MG];
           long long p0 = (DBG ? clock64() : 0ll);
+          // (the operand-source choice is hoisted out of the unrolled loops: inside them it would serialise the loads)
+          if (a.idxT && a.mode == 1) {     // rows and codebook slots from the k-step table (constant bank), bytes from registers
 #pragma unroll
-          for (int i = 0; i < MG; i++) {
-            if (i < n) {
-              if (a.idxT && a.mode == 1) {   // rows and codebook slots from the k-step table (constant bank), bytes from registers
+            for (int i = 0; i < MG; i++) {
+              if (i < n) {
                 const KStep ks = a.tab[e0 + s0 + i];
                 i0x[i] = ks.cb0 * K + ByteOf48(iA0, iA1, iB0, ks.idx0);
                 i1x[i] = ks.cb1 * K + ByteOf48(iA0, iA1, iB0, ks.idx1);
-              } else if (a.idxT) {           // mode 0: k-step = tap s0 + i, codebook slots 0 / 1
+              }
+            }
+          } else if (a.idxT) {             // mode 0: k-step = tap s0 + i, codebook slots 0 / 1
+#pragma unroll
+            for (int i = 0; i < MG; i++) {
+              if (i < n) {
                 i0x[i] = ByteOf32(iA0, iA1, s0 + i);
                 i1x[i] = K + ByteOf32(iB0, iB1, s0 + i);
-              } else {
-                const KStep ks = a.tab[e0 + s0 + i];
-                i0x[i] = ks.cb0 * K + (idb[ks.idx0 * 128] >> a.kshift);
-                i1x[i] = ks.cb1 * K + (idb[ks.idx1 * 128] >> a.kshift);
+              }
+            }
+          } else {                         // table entries and index bytes of all k-steps in flight together
+            KStep ks[MG];
+#pragma unroll
+            for (int i = 0; i < MG; i++)
+              if (i < n) ks[i] = tabS[e0 + s0 + i];
+#pragma unroll
+            for (int i = 0; i < MG; i++) {
+              if (i < n) {
+                i0x[i] = ks[i].cb0 * K + (idb[ks[i].idx0 * 128] >> a.kshift);
+                i1x[i] = ks[i].cb1 * K + (idb[ks[i].idx1 * 128] >> a.kshift);
               }
             }
           }

@@ -7,21 +7,27 @@
 // gather kernels use (reference CaffeEva::CalcFeatMap_ConvAprx / _FCntAprx + GetInPdMat, src/CaffeEva.cc:760-868,
 // 968-1025, 1261-1296, evaluated as x . (decoded w) instead of gather(LUT(x)); same sums, different association).
 //
-// Roles inside a CTA (256 threads, warp-specialised, mbarrier pipelines, no CTA-wide barrier in the main loop):
-//   warps 0-3  decoders: thread = output channel (= TMEM lane).  Per k-step: index byte(s) -> codeword half(s) from the
-//              staged codebook slice -> hi (tf32) / lo (exact remainder) in registers -> tcgen05.st into the A ring in
-//              TMEM (16 columns per k-step: 8 hi + 8 lo).  Decoded weights never touch shared memory.
-//   warp 4     one thread issues tcgen05.mma (kind::tf32, M = 128 channels, N = NT positions, K = 8) with A in TMEM and
-//              B = the position planes in shared memory; three MMAs per k-step (3xTF32: Ah*Bh + Ah*Bl + Al*Bh).
-//   warps 5-7  stagers: the next chunk's positions go global -> registers -> hi/lo planes (K-major, SWIZZLE_NONE core
-//              matrices: 8 positions x 16 B, SBO = 128 B, LBO = distance between the two halves), double-buffered against
-//              the MMAs of the current chunk; codebook slices + index rows by cp.async, four chunks deep.  FC layers: the
-//              planes were pre-split by fc_prep_kernel and arrive by one cp.async.bulk per chunk (three buffers).
+// Roles inside a CTA (warp-specialised, mbarrier pipelines, no CTA-wide barrier in the main loop):
+//   warps 0-3  decoders: thread = output channel (= TMEM lane).  Per k-step: index byte(s) -> codeword piece(s) from the
+//   (+ 8-11)   staged codebook slice -> tcgen05.st into the A ring in TMEM (16 columns per k-step).  Decoded weights never
+//              touch shared memory.  bf16x2 operands (default): the codebook was split into bf16 pieces {w1, w2} once at
+//              layer creation, the decoders convert nothing; conv layers: all tap indices of a chunk sit in registers
+//              (channel-major index block, one or two 128-bit loads per chunk), so a k-step costs ONE dependent
+//              shared-memory round trip (the codeword gather) -- under the MMAs' operand fetch a round trip is ~450 clk.
+//   warp 4     one elected thread issues tcgen05.mma (M = 128 channels, N = NT positions) with A in TMEM and B = the
+//              position planes in shared memory: two kind::f16 MMAs of K = 16 per k-step (bf16x2:
+//              [w1|w1].[x1|x2] + [w2|w2].[x1|x2]) or three kind::tf32 MMAs of K = 8 (3xTF32: Ah*Bh + Ah*Bl + Al*Bh).
+//   warps 5-7  stagers: the next chunk's positions go global -> registers -> planes (K-major, SWIZZLE_NONE core matrices:
+//   (+ 12-15)  8 positions x 16 B, SBO = 128 B, LBO = distance between the two halves / pieces), buffered against the MMAs
+//              of the current chunk (3x3 tiles: two register sets, loads two chunks ahead); a chunk's codebook slices and
+//              index blocks arrive by cp.async.bulk counted on the chunk's mbarrier (3xTF32: cp.async), four chunks deep.
+//              FC layers: the planes were pre-split by fc_prep_kernel and arrive by one cp.async.bulk per chunk.
 //   all warps  epilogue: TMEM (lane = channel, column = position) -> + bias, ReLU -> NHWC stores (a warp writes 32
 //              consecutive channels of one position: 128 B).
-// Shared-memory traffic per k-step is the B operand only (NT x 32 B per MMA = 64 B/clk at the MMA floor) plus the
-// decoders' index / codeword reads, so the tensor pipe, not shared memory, is the limit (the first version of this
-// kernel kept the decoded weights in shared memory and was bound by operand fetch: profiles/README.md, "dec_tc v1").
+// Instantiations: 8 warps (FC tiles, 3xTF32), LITE = 8 warps at <= 128 registers, two CTAs per SM (tiles of <= 128
+// positions), WIDE = 12 warps (second decoder group; conv2-5), XL = 16 warps (second decoder group + seven stager warps;
+// conv1).  What paces the kernel is the latency of shared memory under load (MMA operand fetch + codeword gathers keep the
+// pipe 65-70 % busy), not a throughput limit: profiles/README.md, "Role cycle counters".
 //
 // Layer geometries are expressed as a table of k-steps (KStep: B start / half distance inside the staged planes, index
 // row and codebook slot of either half), so one main loop serves
